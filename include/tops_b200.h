@@ -1,0 +1,171 @@
+/* tops_b200.h — C ABI of libtops_b200.so: a B200 (sm_100a) backend for the hot path of mstksg/tensor-ops,
+ * i.e. evaluating a composed TOp (runTOp / gradTOp) over ffLayer networks.
+ *
+ * The reference has NO C ABI and NO FFI (grep for `foreign import` over /root/reference is empty); its plugin
+ * boundary is two Haskell type-class dictionaries:
+ *     class BLAS   (src/TensorOps/BLAS.hs:90-173)   — what Backend/BTensor.hs dispatches onto
+ *     class Tensor (src/TensorOps/Types.hs:52-109)  — what every TOp closure is written against
+ * Each entry point below names the class method (file:line) it is the device-side body of.  A Haskell
+ * `instance BLAS CuMat` / `instance Tensor CuTensor` binds them with `foreign import ccall`.
+ *
+ * Conventions
+ *   - Every function returns 0 (TOPS_OK) or a tops_status code; it never throws, aborts or exits.
+ *     `tops_last_error(ctx)` returns the message for the last failure on that context.
+ *   - Tensors are immutable, ref-counted device buffers (`tops_buf`), row-major, first index outermost, exactly
+ *     the index order of the reference's type-level dimension lists.  Methods return NEW buffers through
+ *     `tops_buf** out`; if `*out` is non-NULL on entry it must be a buffer of the right shape and is
+ *     written in place (lets callers pre-allocate / pack outputs, e.g. [dW‖db] for one all-reduce).
+ *   - All work is enqueued on the context's stream; nothing synchronises except tops_sync, tops_download
+ *     and tops_index (the reference's observation points `(!)`, `toList`, `indexB`).
+ *   - There is NO CPU fallback: if the CUDA device or the sm_100a kernels are unavailable, tops_init fails.
+ *   - Thread safety: a context may be used from several host threads; calls are serialised by a mutex.
+ */
+#ifndef TOPS_B200_H
+#define TOPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tops_ctx tops_ctx;
+typedef struct tops_buf tops_buf;
+
+typedef enum {
+    TOPS_OK = 0,
+    TOPS_ERR_INVALID = 1,      /* bad argument / NULL */
+    TOPS_ERR_SHAPE = 2,        /* shapes do not conform */
+    TOPS_ERR_CUDA = 3,         /* CUDA runtime / launch failure (message has the CUDA error) */
+    TOPS_ERR_OOM = 4,
+    TOPS_ERR_UNSUPPORTED = 5,
+    TOPS_ERR_NO_DEVICE = 6     /* no sm_100 device: the library refuses to run (no fallback) */
+} tops_status;
+
+typedef enum { TOPS_F32 = 0, TOPS_BF16 = 1 } tops_dtype;
+
+/* How fp32 GEMM-class work (gemm, gmul with |os|>=1 on matrices, the fused ffLayer paths) uses the tensor cores. */
+typedef enum {
+    TOPS_PREC_TF32X3 = 0,  /* default: 3-pass hi/lo TF32 split on tcgen05, fp32-grade accuracy (~1e-6 rel)  */
+    TOPS_PREC_TF32 = 1,    /* single TF32 pass on tcgen05 (~1e-3 rel), the throughput mode                   */
+    TOPS_PREC_FP32_SIMT = 2 /* CUDA-core FFMA kernel (exact fp32 products); also what un-TMA-able strides use */
+} tops_precision;
+
+typedef enum { TOPS_ACT_ID = 0, TOPS_ACT_LOGISTIC = 1, TOPS_ACT_SOFTMAX = 2 } tops_act;
+typedef enum { TOPS_LOSS_NONE = 0, TOPS_LOSS_SQUARED_ERROR = 1, TOPS_LOSS_CROSS_ENTROPY = 2 } tops_loss;
+
+#define TOPS_MAX_RANK 8
+
+/* ------------------------------------------------------------------ lifecycle */
+int tops_init(int device, tops_ctx** ctx);
+int tops_shutdown(tops_ctx* ctx);
+const char* tops_last_error(tops_ctx* ctx);
+int tops_sync(tops_ctx* ctx);
+/* Run on an externally owned CUDA stream (e.g. torch's current stream); NULL restores the context's own stream. */
+int tops_set_stream(tops_ctx* ctx, void* cuda_stream);
+int tops_set_precision(tops_ctx* ctx, int precision);
+int tops_get_precision(tops_ctx* ctx);
+/* number of kernels this library has launched on the context so far (bench.py's gpu_launches) */
+int64_t tops_launch_count(tops_ctx* ctx);
+int tops_device_sm_count(tops_ctx* ctx);
+
+/* ------------------------------------------------------------------ storage
+ * replaces: hmatrix Storable Vector/Matrix allocation inside every HMat method (BLAS/HMat.hs:37-39),
+ *           `generateA` / `genRand` / `fromList` / `toList` / `(!)` (Types.hs:93-109, Backend/BTensor.hs:838-858). */
+int tops_buf_alloc(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, tops_buf** out);
+/* non-owning view of device memory the caller allocated (torch tensor, cudaMalloc); caller keeps it alive */
+int tops_buf_wrap(tops_ctx* ctx, void* device_ptr, int dtype, int rank, const int64_t* dims, tops_buf** out);
+/* contiguous sub-range view: `offset` elements into `parent`, new shape; keeps parent alive */
+int tops_buf_view(tops_ctx* ctx, tops_buf* parent, int64_t offset, int rank, const int64_t* dims, tops_buf** out);
+int tops_buf_retain(tops_buf* b);
+int tops_buf_release(tops_buf* b);     /* stream-ordered free when the count reaches 0 */
+int tops_buf_rank(const tops_buf* b);
+int tops_buf_dims(const tops_buf* b, int64_t* dims_out);   /* writes rank entries */
+int tops_buf_dtype(const tops_buf* b);
+int64_t tops_buf_numel(const tops_buf* b);
+void* tops_buf_data(const tops_buf* b);                     /* device pointer */
+int tops_upload(tops_ctx* ctx, tops_buf* dst, const void* host, size_t bytes);      /* H2D, async if host is pinned */
+int tops_download(tops_ctx* ctx, const tops_buf* src, void* host, size_t bytes);    /* D2H + stream sync */
+int tops_fill(tops_ctx* ctx, tops_buf* dst, double value);                          /* TT.konst, Tensor.hs:49-54 */
+int tops_rand_normal(tops_ctx* ctx, tops_buf* dst, double mean, double stddev, uint64_t seed);   /* genRand (normalDistr ..), FeedForward.hs:206-207 */
+int tops_rand_uniform(tops_ctx* ctx, tops_buf* dst, double lo, double hi, uint64_t seed);        /* genRand (uniformDistr ..), Dots.hs:63 */
+int tops_cast(tops_ctx* ctx, const tops_buf* x, int dtype, tops_buf** out);
+
+/* ------------------------------------------------------------------ class BLAS, method for method (BLAS.hs:90-173;
+ * reference bodies BLAS/HMat.hs:103-231).  Vectors are rank-1, matrices rank-2 row-major.  y/c operands may be NULL
+ * (the reference's `Maybe`). */
+int tops_axpy(tops_ctx*, double alpha, const tops_buf* x, const tops_buf* y, tops_buf** out);                 /* BLAS.hs:97-101  HMat.hs:135-139 */
+int tops_dot(tops_ctx*, const tops_buf* x, const tops_buf* y, tops_buf** out_scalar);                         /* BLAS.hs:102-104 HMat.hs:141-142 */
+int tops_ger(tops_ctx*, const tops_buf* x, const tops_buf* y, tops_buf** out);                                /* BLAS.hs:108-110 HMat.hs:144-145 */
+int tops_gemv(tops_ctx*, double alpha, const tops_buf* a, const tops_buf* x, double beta, const tops_buf* y, tops_buf** out);   /* BLAS.hs:111-116 HMat.hs:147-153 */
+int tops_gemm(tops_ctx*, double alpha, const tops_buf* a, const tops_buf* b, double beta, const tops_buf* c, tops_buf** out);   /* BLAS.hs:118-123 HMat.hs:154-160 */
+int tops_scale(tops_ctx*, double alpha, const tops_buf* x, tops_buf** out);                                   /* scaleB BLAS.hs:124-127 / scaleT Types.hs:70 */
+int tops_add(tops_ctx*, const tops_buf* x, const tops_buf* y, tops_buf** out);                                /* addB BLAS.hs:128 — a plain add, not the reference's gemm-with-identity (BTensor.hs:113) */
+int tops_index(tops_ctx*, const tops_buf* x, const int64_t* idx, double* value_out);                          /* indexB BLAS.hs:129-132 / (!) Types.hs:107-109; synchronises */
+int tops_index_row(tops_ctx*, const tops_buf* a, int64_t i, tops_buf** out);                                  /* indexRowB BLAS.hs:133-136 (view, no copy) */
+int tops_transp(tops_ctx*, const tops_buf* a, tops_buf** out);                                                /* transpB BLAS.hs:137-139 / transp Types.hs:71-73: reverses ALL axes */
+int tops_eye(tops_ctx*, int64_t n, tops_buf** out);                                                           /* BLAS.hs:158-159 */
+int tops_trace(tops_ctx*, const tops_buf* a, tops_buf** out_scalar);                                          /* traceB BLAS.hs:160-162 */
+int tops_diag(tops_ctx*, int rank, const tops_buf* v, tops_buf** out);                                        /* diagB BLAS.hs:163-165 / diag Types.hs:85-88 (rank-n generalised diagonal) */
+int tops_get_diag(tops_ctx*, const tops_buf* a, tops_buf** out);                                              /* getDiagB BLAS.hs:166-168 / getDiag Types.hs:89-92 */
+int tops_sum(tops_ctx*, const tops_buf* x, tops_buf** out_scalar);                                            /* sumB BLAS.hs:169-171 */
+
+/* liftB / liftT (BLAS.hs:92-96, Types.hs:56-59): n-ary elementwise map.  The reference passes a host closure
+ * `Vec n a -> a`; a device cannot call it per element, so the closure is reified by applying it to symbolic
+ * variables on the host side and shipping the expression as postfix bytecode (see TOPS_OP_* below).
+ * Known programs (logistic, d*logistic'(x), exp, recip, log, p - r*g, ...) are matched to fused kernels; anything
+ * else runs in a per-thread stack interpreter — still on the device, never on the host. */
+int tops_lift(tops_ctx*, const int32_t* prog, int prog_len, const float* consts, int n_consts,
+              int n_in, const tops_buf* const* in, int rank, const int64_t* dims, tops_buf** out);
+
+enum {
+    TOPS_OP_VAR = 0,    /* arg: input index      push in[arg][i]      */
+    TOPS_OP_CONST = 1,  /* arg: constant index   push consts[arg]     */
+    TOPS_OP_ADD = 2, TOPS_OP_SUB = 3, TOPS_OP_MUL = 4, TOPS_OP_DIV = 5,
+    TOPS_OP_NEG = 6, TOPS_OP_EXP = 7, TOPS_OP_LOG = 8, TOPS_OP_RECIP = 9,
+    TOPS_OP_SQRT = 10, TOPS_OP_TANH = 11, TOPS_OP_ABS = 12, TOPS_OP_SIGNUM = 13,
+    TOPS_OP_MAX = 14, TOPS_OP_MIN = 15, TOPS_OP_POW = 16, TOPS_OP_LOGISTIC = 17,
+    TOPS_OP_SIN = 18, TOPS_OP_COS = 19
+};
+/* each instruction is one int32: (opcode << 16) | arg */
+
+/* ------------------------------------------------------------------ class Tensor beyond BLAS (Types.hs:52-109) */
+/* gmul (Types.hs:60-66; semantics Data/Nested.hs:451-473):  x : ms++os, y : Reverse os ++ ns  ->  ms++ns,
+ *   z[m..,n..] = sum_{o..} x[m..,o..] * y[reverse(o..),n..].   Replaces BTensor.gmulB/gmulBLAS/naiveGMul
+ *   (Backend/BTensor.hs:592-716) with one tensor-core GEMM on flat storage (plus an axis permutation when |os|>=2). */
+int tops_gmul(tops_ctx*, int len_m, int len_o, int len_n, const tops_buf* x, const tops_buf* y, tops_buf** out);
+int tops_sum_t(tops_ctx*, int n, const tops_buf* const* xs, tops_buf** out);                                  /* sumT Types.hs:69 (left fold, in order) */
+int tops_sum_rows(tops_ctx*, const tops_buf* x, tops_buf** out);                                              /* sumRows Types.hs:82-84 */
+int tops_broadcast_rows(tops_ctx*, int64_t n, const tops_buf* row, tops_buf** out);                           /* mapRows (LS LZ) (const row): VJP of sumRows, TOp.hs:151-159 */
+int tops_map_rows_softmax(tops_ctx*, const tops_buf* x, tops_buf** out);                                      /* mapRows over the leading axis of the reference's softmax TOp (NeuralNet.hs:52-59) */
+
+/* ------------------------------------------------------------------ fused, batched hot path
+ * Batched semantics: for each sample s evaluate runTOp and gradTOp' of the per-sample TOp
+ *   ffLayer' >>> act      (FeedForward.hs:209-212, NeuralNet.hs:38-40)
+ * with parameters fixed; outputs per sample, parameter gradients SUMMED over samples.
+ *   X[B,i] W[o,i] b[o] dA[B,o]  ->  A[B,o] dX[B,i] dW[o,i] db[o]
+ *   Z = X W^T + 1 b^T ; A = act(Z) ; dZ = dA ⊙ act'(Z) ; dW = dZ^T X ; db = Σ_s dZ[s,:] ; dX = dZ W        */
+int tops_fflayer_fwd(tops_ctx*, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act, tops_buf** A);
+/* gradTOp' of the layer: recomputes the forward unless the saved activation `A_saved` is given (Types.hs:155 recomputes) */
+int tops_fflayer_grad(tops_ctx*, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act,
+                      const tops_buf* dA, const tops_buf* A_saved, tops_buf** dX, tops_buf** dW, tops_buf** db);
+/* forward + VJP in one call; the activation and dZ never leave the device and are produced by one GEMM epilogue */
+int tops_fflayer_fwd_grad(tops_ctx*, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act,
+                          const tops_buf* dA, tops_buf** A, tops_buf** dX, tops_buf** dW, tops_buf** db);
+/* netGrad (FeedForward.hs:178-199) of a genNet-style network (FeedForward.hs:216-235) over a batch:
+ *   layers l = 0..n-1 with W[l], b[l], acts[l]; loss on (A_out, Y); per-sample losses summed into loss_sum (rank 0).
+ *   Outputs: A_out[B,o], loss_sum[], dX[B,i] (may be NULL to skip), dW[l], db[l]. */
+int tops_mlp_fwd_grad(tops_ctx*, int n_layers, const tops_buf* const* W, const tops_buf* const* b, const int* acts, int loss,
+                      const tops_buf* X, const tops_buf* Y, tops_buf** A_out, tops_buf** loss_sum, tops_buf** dX,
+                      tops_buf** dW, tops_buf** db);
+/* runNetwork over a batch (FeedForward.hs:123-129) */
+int tops_mlp_fwd(tops_ctx*, int n_layers, const tops_buf* const* W, const tops_buf* const* b, const int* acts,
+                 const tops_buf* X, tops_buf** A_out);
+/* trainNetwork's parameter step  p' = p - r*g  (FeedForward.hs:141-147), for n parameter tensors at once */
+int tops_sgd_step(tops_ctx*, int n, const tops_buf* const* params, const tops_buf* const* grads, double rate, tops_buf** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPS_B200_H */

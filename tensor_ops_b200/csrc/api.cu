@@ -1,0 +1,928 @@
+// C ABI of libtops_b200 (include/tops_b200.h): contexts, ref-counted device tensors, the BLAS / Tensor class
+// methods of tensor-ops as device operations, and the fused batched ffLayer / MLP forward+gradient paths.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gemm_sm100.cuh"
+#include "gemm_sm100.h"
+#include "kernels.h"
+#include "tops_b200.h"
+
+using namespace tops;
+
+struct tops_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::recursive_mutex mu;
+    std::string last_error;
+    int precision = TOPS_PREC_TF32X3;
+    int64_t launches = 0;
+    unsigned int* wd_host = nullptr;
+    unsigned int* wd_dev = nullptr;
+    float* scratch = nullptr;   // small persistent workspace for reductions (1 MiB)
+};
+
+struct tops_buf {
+    tops_ctx* ctx;
+    std::atomic<int> refs;
+    int dtype;
+    int rank;
+    int64_t dims[TOPS_MAX_RANK];   // logical dims
+    int64_t numel;
+    void* data;
+    bool owns;
+    bool tr;           // rank-2 only: storage is the row-major TRANSPOSE of the logical matrix (O(1) transp, like hmatrix `tr`)
+    tops_buf* parent;  // kept alive while this view lives
+};
+
+namespace {
+
+constexpr size_t kScratchBytes = 4u << 20;
+
+int set_err(tops_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    return code;
+}
+
+#define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu)
+#define CHECK_CTX(ctx) do { if (!(ctx)) return TOPS_ERR_INVALID; } while (0)
+#define CUDA_TRY(ctx, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return set_err(ctx, TOPS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
+#define TRY(expr) do { int r_ = (expr); if (r_ != TOPS_OK) return r_; } while (0)
+
+size_t esize(int dtype) { return dtype == TOPS_BF16 ? 2 : 4; }
+
+k::LaunchCtx lc_of(tops_ctx* ctx) { return k::LaunchCtx{ctx->stream, ctx->num_sms, &ctx->launches}; }
+
+int check_launch(tops_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(ctx, TOPS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return TOPS_OK;
+}
+
+int new_buf(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, void* data, bool owns, tops_buf* parent, tops_buf** out) {
+    if (rank < 0 || rank > TOPS_MAX_RANK) return set_err(ctx, TOPS_ERR_INVALID, "rank %d out of range", rank);
+    tops_buf* b = new tops_buf();
+    b->ctx = ctx; b->refs = 1; b->dtype = dtype; b->rank = rank; b->numel = 1;
+    for (int i = 0; i < rank; ++i) {
+        if (dims[i] < 0) { delete b; return set_err(ctx, TOPS_ERR_INVALID, "negative dimension"); }
+        b->dims[i] = dims[i]; b->numel *= dims[i];
+    }
+    b->data = data; b->owns = owns; b->tr = false; b->parent = parent;
+    if (parent) parent->refs.fetch_add(1);
+    *out = b;
+    return TOPS_OK;
+}
+
+int alloc_buf(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, tops_buf** out) {
+    int64_t n = 1;
+    for (int i = 0; i < rank; ++i) n *= dims[i];
+    void* p = nullptr;
+    size_t bytes = (size_t)(n > 0 ? n : 1) * esize(dtype);
+    cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(ctx, e == cudaErrorMemoryAllocation ? TOPS_ERR_OOM : TOPS_ERR_CUDA, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    int r = new_buf(ctx, dtype, rank, dims, p, true, nullptr, out);
+    if (r != TOPS_OK) cudaFreeAsync(p, ctx->stream);
+    return r;
+}
+
+void release_buf(tops_buf* b) {
+    while (b) {
+        if (b->refs.fetch_sub(1) != 1) return;
+        tops_buf* parent = b->parent;
+        if (b->owns && b->data) cudaFreeAsync(b->data, b->ctx->stream);
+        delete b;
+        b = parent;
+    }
+}
+
+struct Tmp {   // RAII holder for temporaries created inside one API call
+    std::vector<tops_buf*> v;
+    ~Tmp() { for (auto* b : v) release_buf(b); }
+    tops_buf* keep(tops_buf* b) { v.push_back(b); return b; }
+};
+
+bool same_shape(const tops_buf* a, const tops_buf* b) {
+    if (a->rank != b->rank) return false;
+    for (int i = 0; i < a->rank; ++i) if (a->dims[i] != b->dims[i]) return false;
+    return true;
+}
+
+// Output protocol: *out == NULL -> allocate; otherwise validate and write in place.
+int prep_out(tops_ctx* ctx, tops_buf** out, int dtype, int rank, const int64_t* dims, bool* fresh = nullptr) {
+    if (!out) return set_err(ctx, TOPS_ERR_INVALID, "NULL output slot");
+    if (fresh) *fresh = (*out == nullptr);
+    if (*out == nullptr) return alloc_buf(ctx, dtype, rank, dims, out);
+    tops_buf* o = *out;
+    if (o->tr) return set_err(ctx, TOPS_ERR_INVALID, "pre-allocated output must not be a transposed view");
+    if (o->dtype != dtype) return set_err(ctx, TOPS_ERR_SHAPE, "pre-allocated output has dtype %d, expected %d", o->dtype, dtype);
+    int64_t n = 1;
+    for (int i = 0; i < rank; ++i) n *= dims[i];
+    if (o->numel != n) return set_err(ctx, TOPS_ERR_SHAPE, "pre-allocated output has %lld elements, expected %lld", (long long)o->numel, (long long)n);
+    return TOPS_OK;
+}
+
+// contiguous (non-transposed) version of x; returns x itself (retained) when already contiguous
+int contig(tops_ctx* ctx, const tops_buf* x, Tmp& tmp, const tops_buf** out) {
+    if (!x->tr) { *out = x; return TOPS_OK; }
+    if (x->dtype != TOPS_F32) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "transposed bf16 view cannot be materialised");
+    tops_buf* t = nullptr;
+    TRY(alloc_buf(ctx, x->dtype, x->rank, x->dims, &t));
+    tmp.keep(t);
+    // storage is [dims1, dims0] row-major; logical [dims0, dims1] = transpose of storage
+    k::transpose2d(lc_of(ctx), (const float*)x->data, (float*)t->data, x->dims[1], x->dims[0]);
+    *out = t;
+    return check_launch(ctx, "transpose");
+}
+
+int need_f32(tops_ctx* ctx, const tops_buf* x, const char* what) {
+    if (!x) return set_err(ctx, TOPS_ERR_INVALID, "%s: NULL tensor", what);
+    if (x->dtype != TOPS_F32) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "%s: only fp32 tensors are supported here", what);
+    return TOPS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- GEMM dispatch
+int run_gemm(tops_ctx* ctx, GemmCall c) {
+    if (c.M <= 0 || c.N <= 0) return TOPS_OK;
+    if (c.epi == EPI_ATOMIC) {
+        CUDA_TRY(ctx, cudaMemsetAsync(c.out0, 0, sizeof(float) * (size_t)c.M * (size_t)c.ld_out0, ctx->stream));
+    }
+    if (c.K <= 0) {   // empty contraction: result is the epilogue applied to zeros; only plain store/atomic make sense
+        if (c.epi == EPI_STORE && !c.aux0) CUDA_TRY(ctx, cudaMemsetAsync(c.out0, 0, esize(c.io_bf16 ? TOPS_BF16 : TOPS_F32) * (size_t)c.M * (size_t)c.ld_out0, ctx->stream));
+        if (c.epi == EPI_STORE || c.epi == EPI_ATOMIC) return TOPS_OK;
+        return set_err(ctx, TOPS_ERR_SHAPE, "gemm: empty contraction dimension");
+    }
+    const bool want_umma = c.dtype == 1 || ctx->precision != TOPS_PREC_FP32_SIMT;
+    if (want_umma) {
+        c.passes = (c.dtype == 0 && ctx->precision == TOPS_PREC_TF32X3) ? 3 : 1;
+        char err[256];
+        int r = gemm_umma_launch(c, ctx->stream, ctx->wd_dev, ctx->num_sms, err, sizeof err);
+        if (r == 0) { ++ctx->launches; return TOPS_OK; }
+        if (r > 0) return set_err(ctx, TOPS_ERR_CUDA, "%s", err);
+        if (c.dtype == 1) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "bf16 gemm needs 16-byte aligned operands with strides that are multiples of 8 elements (%s)", err);
+    }
+    int r = k::gemm_simt(lc_of(ctx), c);
+    if (r != 0) return set_err(ctx, TOPS_ERR_CUDA, "simt gemm launch failed (%d)", r);
+    return TOPS_OK;
+}
+
+// describe a rank-2 fp32/bf16 matrix (possibly a transposed view) as a GEMM operand whose reduction runs over `k_axis`
+// of its LOGICAL shape.  Returns pointer/ld/major for the engine's  sum_k P(mn, k)  convention.
+void as_operand(const tops_buf* m, int k_axis, const void** ptr, long long* ld, int* major) {
+    // logical [d0, d1]; stored row-major as [d0,d1] (tr=0) or [d1,d0] (tr=1)
+    const bool k_is_contiguous = (k_axis == 1) != m->tr;
+    *ptr = m->data;
+    *ld = m->tr ? m->dims[0] : m->dims[1];
+    *major = k_is_contiguous ? MAJOR_K : MAJOR_MN;
+}
+
+}  // namespace
+
+// ================================================================================================ lifecycle
+extern "C" int tops_init(int device, tops_ctx** out) {
+    if (!out) return TOPS_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return TOPS_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TOPS_ERR_NO_DEVICE;
+    if (prop.major != 10) return TOPS_ERR_NO_DEVICE;   // sm_100a kernels only; there is no fallback path
+    if (cudaSetDevice(device) != cudaSuccess) return TOPS_ERR_CUDA;
+    tops_ctx* ctx = new tops_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return TOPS_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if (cudaHostAlloc((void**)&ctx->wd_host, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->wd_dev, ctx->wd_host, 0) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->scratch, kScratchBytes) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return TOPS_ERR_CUDA;
+    }
+    memset(ctx->wd_host, 0, 64);
+    *out = ctx;
+    return TOPS_OK;
+}
+
+extern "C" int tops_shutdown(tops_ctx* ctx) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->wd_host) cudaFreeHost(ctx->wd_host);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return TOPS_OK;
+}
+
+extern "C" const char* tops_last_error(tops_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "NULL context"; }
+
+extern "C" int tops_sync(tops_ctx* ctx) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess)
+        return set_err(ctx, TOPS_ERR_CUDA, "stream sync failed: %s (gemm watchdog code=0x%x cta=%u)", cudaGetErrorString(e), ctx->wd_host[0], ctx->wd_host[1]);
+    return TOPS_OK;
+}
+extern "C" int tops_set_stream(tops_ctx* ctx, void* s) { CHECK_CTX(ctx); LOCK(ctx); ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return TOPS_OK; }
+extern "C" int tops_set_precision(tops_ctx* ctx, int p) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (p < 0 || p > 2) return set_err(ctx, TOPS_ERR_INVALID, "unknown precision %d", p);
+    ctx->precision = p;
+    return TOPS_OK;
+}
+extern "C" int tops_get_precision(tops_ctx* ctx) { return ctx ? ctx->precision : -1; }
+extern "C" int64_t tops_launch_count(tops_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int tops_device_sm_count(tops_ctx* ctx) { return ctx ? ctx->num_sms : -1; }
+
+// ================================================================================================ storage
+extern "C" int tops_buf_alloc(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!out || (rank > 0 && !dims)) return set_err(ctx, TOPS_ERR_INVALID, "tops_buf_alloc: NULL argument");
+    if (dtype != TOPS_F32 && dtype != TOPS_BF16) return set_err(ctx, TOPS_ERR_INVALID, "unknown dtype %d", dtype);
+    *out = nullptr;
+    return alloc_buf(ctx, dtype, rank, dims, out);
+}
+extern "C" int tops_buf_wrap(tops_ctx* ctx, void* p, int dtype, int rank, const int64_t* dims, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!out || !p) return set_err(ctx, TOPS_ERR_INVALID, "tops_buf_wrap: NULL argument");
+    return new_buf(ctx, dtype, rank, dims, p, false, nullptr, out);
+}
+extern "C" int tops_buf_view(tops_ctx* ctx, tops_buf* parent, int64_t offset, int rank, const int64_t* dims, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!parent || !out) return set_err(ctx, TOPS_ERR_INVALID, "tops_buf_view: NULL argument");
+    if (parent->tr) return set_err(ctx, TOPS_ERR_INVALID, "cannot take a flat view of a transposed view");
+    int64_t n = 1;
+    for (int i = 0; i < rank; ++i) n *= dims[i];
+    if (offset < 0 || offset + n > parent->numel) return set_err(ctx, TOPS_ERR_SHAPE, "view [%lld, %lld) exceeds parent of %lld elements", (long long)offset, (long long)(offset + n), (long long)parent->numel);
+    return new_buf(ctx, parent->dtype, rank, dims, (char*)parent->data + offset * esize(parent->dtype), false, parent, out);
+}
+extern "C" int tops_buf_retain(tops_buf* b) { if (!b) return TOPS_ERR_INVALID; b->refs.fetch_add(1); return TOPS_OK; }
+extern "C" int tops_buf_release(tops_buf* b) {
+    if (!b) return TOPS_ERR_INVALID;
+    tops_ctx* ctx = b->ctx; LOCK(ctx);
+    release_buf(b);
+    return TOPS_OK;
+}
+extern "C" int tops_buf_rank(const tops_buf* b) { return b ? b->rank : -1; }
+extern "C" int tops_buf_dims(const tops_buf* b, int64_t* d) { if (!b || !d) return TOPS_ERR_INVALID; for (int i = 0; i < b->rank; ++i) d[i] = b->dims[i]; return TOPS_OK; }
+extern "C" int tops_buf_dtype(const tops_buf* b) { return b ? b->dtype : -1; }
+extern "C" int64_t tops_buf_numel(const tops_buf* b) { return b ? b->numel : -1; }
+extern "C" void* tops_buf_data(const tops_buf* b) { return b ? b->data : nullptr; }
+
+extern "C" int tops_upload(tops_ctx* ctx, tops_buf* dst, const void* host, size_t bytes) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!dst || (!host && bytes)) return set_err(ctx, TOPS_ERR_INVALID, "tops_upload: NULL argument");
+    if (dst->tr) return set_err(ctx, TOPS_ERR_INVALID, "cannot upload into a transposed view");
+    if (bytes != (size_t)dst->numel * esize(dst->dtype)) return set_err(ctx, TOPS_ERR_SHAPE, "upload of %zu bytes into a tensor of %zu bytes", bytes, (size_t)dst->numel * esize(dst->dtype));
+    if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(dst->data, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return TOPS_OK;
+}
+extern "C" int tops_download(tops_ctx* ctx, const tops_buf* src, void* host, size_t bytes) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!src || (!host && bytes)) return set_err(ctx, TOPS_ERR_INVALID, "tops_download: NULL argument");
+    Tmp tmp; const tops_buf* s;
+    TRY(contig(ctx, src, tmp, &s));
+    if (bytes != (size_t)s->numel * esize(s->dtype)) return set_err(ctx, TOPS_ERR_SHAPE, "download of %zu bytes from a tensor of %zu bytes", bytes, (size_t)s->numel * esize(s->dtype));
+    if (bytes) CUDA_TRY(ctx, cudaMemcpyAsync(host, s->data, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return tops_sync(ctx);
+}
+extern "C" int tops_fill(tops_ctx* ctx, tops_buf* dst, double v) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!dst) return set_err(ctx, TOPS_ERR_INVALID, "tops_fill: NULL tensor");
+    if (dst->dtype == TOPS_BF16) k::fill_bf16(lc_of(ctx), dst->data, dst->numel, (float)v);
+    else k::fill(lc_of(ctx), (float*)dst->data, dst->numel, (float)v);
+    return check_launch(ctx, "fill");
+}
+extern "C" int tops_rand_normal(tops_ctx* ctx, tops_buf* dst, double mean, double sd, uint64_t seed) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, dst, "tops_rand_normal"));
+    k::rand_normal(lc_of(ctx), (float*)dst->data, dst->numel, (float)mean, (float)sd, seed);
+    return check_launch(ctx, "rand_normal");
+}
+extern "C" int tops_rand_uniform(tops_ctx* ctx, tops_buf* dst, double lo, double hi, uint64_t seed) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, dst, "tops_rand_uniform"));
+    k::rand_uniform(lc_of(ctx), (float*)dst->data, dst->numel, (float)lo, (float)hi, seed);
+    return check_launch(ctx, "rand_uniform");
+}
+extern "C" int tops_cast(tops_ctx* ctx, const tops_buf* x, int dtype, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!x) return set_err(ctx, TOPS_ERR_INVALID, "tops_cast: NULL tensor");
+    Tmp tmp; const tops_buf* s;
+    TRY(contig(ctx, x, tmp, &s));
+    TRY(prep_out(ctx, out, dtype, s->rank, s->dims));
+    if (s->dtype == dtype) CUDA_TRY(ctx, cudaMemcpyAsync((*out)->data, s->data, (size_t)s->numel * esize(dtype), cudaMemcpyDeviceToDevice, ctx->stream));
+    else if (dtype == TOPS_BF16) k::cast_f32_bf16(lc_of(ctx), (const float*)s->data, (*out)->data, s->numel);
+    else k::cast_bf16_f32(lc_of(ctx), s->data, (float*)(*out)->data, s->numel);
+    return check_launch(ctx, "cast");
+}
+
+// ================================================================================================ class BLAS
+extern "C" int tops_axpy(tops_ctx* ctx, double alpha, const tops_buf* x, const tops_buf* y, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, x, "tops_axpy"));
+    if (y) { TRY(need_f32(ctx, y, "tops_axpy")); if (y->numel != x->numel) return set_err(ctx, TOPS_ERR_SHAPE, "axpy: x has %lld elements, y has %lld", (long long)x->numel, (long long)y->numel); }
+    Tmp tmp; const tops_buf *xs, *ys = nullptr;
+    TRY(contig(ctx, x, tmp, &xs));
+    if (y) TRY(contig(ctx, y, tmp, &ys));
+    TRY(prep_out(ctx, out, TOPS_F32, xs->rank, xs->dims));
+    k::axpy(lc_of(ctx), (float)alpha, (const float*)xs->data, ys ? (const float*)ys->data : nullptr, (float*)(*out)->data, xs->numel);
+    return check_launch(ctx, "axpy");
+}
+extern "C" int tops_scale(tops_ctx* ctx, double alpha, const tops_buf* x, tops_buf** out) { return tops_axpy(ctx, alpha, x, nullptr, out); }
+extern "C" int tops_add(tops_ctx* ctx, const tops_buf* x, const tops_buf* y, tops_buf** out) {
+    CHECK_CTX(ctx);
+    if (!y) return set_err(ctx, TOPS_ERR_INVALID, "tops_add: NULL tensor");
+    return tops_axpy(ctx, 1.0, x, y, out);
+}
+extern "C" int tops_dot(tops_ctx* ctx, const tops_buf* x, const tops_buf* y, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, x, "tops_dot")); TRY(need_f32(ctx, y, "tops_dot"));
+    if (x->numel != y->numel) return set_err(ctx, TOPS_ERR_SHAPE, "dot: %lld vs %lld elements", (long long)x->numel, (long long)y->numel);
+    Tmp tmp; const tops_buf *xs, *ys;
+    TRY(contig(ctx, x, tmp, &xs)); TRY(contig(ctx, y, tmp, &ys));
+    TRY(prep_out(ctx, out, TOPS_F32, 0, nullptr));
+    k::dot(lc_of(ctx), (const float*)xs->data, (const float*)ys->data, xs->numel, (float*)(*out)->data, ctx->scratch);
+    return check_launch(ctx, "dot");
+}
+extern "C" int tops_sum(tops_ctx* ctx, const tops_buf* x, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, x, "tops_sum"));
+    TRY(prep_out(ctx, out, TOPS_F32, 0, nullptr));
+    k::sum_all(lc_of(ctx), (const float*)x->data, x->numel, (float*)(*out)->data, ctx->scratch);   // order-insensitive: tr irrelevant
+    return check_launch(ctx, "sum");
+}
+extern "C" int tops_ger(tops_ctx* ctx, const tops_buf* x, const tops_buf* y, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, x, "tops_ger")); TRY(need_f32(ctx, y, "tops_ger"));
+    if (x->rank != 1 || y->rank != 1) return set_err(ctx, TOPS_ERR_SHAPE, "ger: operands must be vectors");
+    int64_t d[2] = {x->dims[0], y->dims[0]};
+    TRY(prep_out(ctx, out, TOPS_F32, 2, d));
+    k::ger(lc_of(ctx), (const float*)x->data, (const float*)y->data, (float*)(*out)->data, d[0], d[1]);
+    return check_launch(ctx, "ger");
+}
+extern "C" int tops_gemv(tops_ctx* ctx, double alpha, const tops_buf* a, const tops_buf* x, double beta, const tops_buf* y, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, a, "tops_gemv")); TRY(need_f32(ctx, x, "tops_gemv"));
+    if (a->rank != 2 || x->rank != 1 || a->dims[1] != x->dims[0]) return set_err(ctx, TOPS_ERR_SHAPE, "gemv: A[%lld,%lld] x[%lld]", (long long)(a->rank == 2 ? a->dims[0] : -1), (long long)(a->rank == 2 ? a->dims[1] : -1), (long long)x->numel);
+    if (y) { TRY(need_f32(ctx, y, "tops_gemv")); if (y->numel != a->dims[0]) return set_err(ctx, TOPS_ERR_SHAPE, "gemv: y has %lld elements, expected %lld", (long long)y->numel, (long long)a->dims[0]); }
+    int64_t d[1] = {a->dims[0]};
+    TRY(prep_out(ctx, out, TOPS_F32, 1, d));
+    k::gemv(lc_of(ctx), (float)alpha, (const float*)a->data, a->tr ? 1 : 0, (const float*)x->data, (float)beta, y ? (const float*)y->data : nullptr, (float*)(*out)->data, a->dims[0], a->dims[1]);
+    return check_launch(ctx, "gemv");
+}
+extern "C" int tops_gemm(tops_ctx* ctx, double alpha, const tops_buf* a, const tops_buf* b, double beta, const tops_buf* c, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, a, "tops_gemm")); TRY(need_f32(ctx, b, "tops_gemm"));
+    if (a->rank != 2 || b->rank != 2 || a->dims[1] != b->dims[0]) return set_err(ctx, TOPS_ERR_SHAPE, "gemm: inner dimensions do not agree");
+    Tmp tmp; const tops_buf* cs = nullptr;
+    if (c) {
+        TRY(need_f32(ctx, c, "tops_gemm"));
+        if (c->rank != 2 || c->dims[0] != a->dims[0] || c->dims[1] != b->dims[1]) return set_err(ctx, TOPS_ERR_SHAPE, "gemm: C has the wrong shape");
+        TRY(contig(ctx, c, tmp, &cs));
+    }
+    int64_t d[2] = {a->dims[0], b->dims[1]};
+    TRY(prep_out(ctx, out, TOPS_F32, 2, d));
+    GemmCall g{};
+    g.dtype = 0; g.M = (int)d[0]; g.N = (int)d[1]; g.K = (int)a->dims[1];
+    as_operand(a, 1, &g.A, &g.lda, &g.major_a);
+    as_operand(b, 0, &g.B, &g.ldb, &g.major_b);
+    g.epi = EPI_STORE; g.alpha = (float)alpha; g.beta = (float)beta;
+    g.out0 = (*out)->data; g.ld_out0 = d[1];
+    if (cs) { g.aux0 = cs->data; g.ld_aux0 = d[1]; }
+    return run_gemm(ctx, g);
+}
+extern "C" int tops_index(tops_ctx* ctx, const tops_buf* x, const int64_t* idx, double* value) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!x || !value || (x->rank > 0 && !idx)) return set_err(ctx, TOPS_ERR_INVALID, "tops_index: NULL argument");
+    int64_t off = 0;
+    if (x->tr) {
+        if (idx[0] < 0 || idx[0] >= x->dims[0] || idx[1] < 0 || idx[1] >= x->dims[1]) return set_err(ctx, TOPS_ERR_SHAPE, "index out of range");
+        off = idx[1] * x->dims[0] + idx[0];
+    } else {
+        for (int i = 0; i < x->rank; ++i) {
+            if (idx[i] < 0 || idx[i] >= x->dims[i]) return set_err(ctx, TOPS_ERR_SHAPE, "index out of range");
+            off = off * x->dims[i] + idx[i];
+        }
+    }
+    if (x->dtype == TOPS_F32) {
+        float v;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&v, (const float*)x->data + off, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(tops_sync(ctx));
+        *value = v;
+    } else {
+        uint16_t h;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&h, (const uint16_t*)x->data + off, 2, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(tops_sync(ctx));
+        uint32_t u = (uint32_t)h << 16; float v; memcpy(&v, &u, 4);
+        *value = v;
+    }
+    return TOPS_OK;
+}
+extern "C" int tops_index_row(tops_ctx* ctx, const tops_buf* a, int64_t i, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!a || !out) return set_err(ctx, TOPS_ERR_INVALID, "tops_index_row: NULL argument");
+    if (a->rank < 1 || i < 0 || i >= a->dims[0]) return set_err(ctx, TOPS_ERR_SHAPE, "row index out of range");
+    Tmp tmp; const tops_buf* s;
+    TRY(contig(ctx, a, tmp, &s));
+    const int64_t row = s->numel / s->dims[0];
+    *out = nullptr;
+    return new_buf(ctx, s->dtype, s->rank - 1, s->dims + 1, (char*)s->data + i * row * esize(s->dtype), false, const_cast<tops_buf*>(s), out);
+}
+extern "C" int tops_transp(tops_ctx* ctx, const tops_buf* a, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!a || !out) return set_err(ctx, TOPS_ERR_INVALID, "tops_transp: NULL argument");
+    if (a->rank <= 2 && *out == nullptr) {   // O(1): rank <= 1 is the identity, rank 2 flips the storage flag (hmatrix `tr`, HMat.hs:175)
+        int64_t d[2] = {0, 0};
+        for (int i = 0; i < a->rank; ++i) d[i] = a->dims[a->rank - 1 - i];
+        TRY(new_buf(ctx, a->dtype, a->rank, d, a->data, false, const_cast<tops_buf*>(a), out));
+        (*out)->tr = a->rank == 2 ? !a->tr : false;
+        return TOPS_OK;
+    }
+    TRY(need_f32(ctx, a, "tops_transp"));
+    int64_t d[TOPS_MAX_RANK]; int perm[TOPS_MAX_RANK];
+    for (int i = 0; i < a->rank; ++i) { d[i] = a->dims[a->rank - 1 - i]; perm[i] = a->rank - 1 - i; }
+    TRY(prep_out(ctx, out, TOPS_F32, a->rank, d));
+    if (a->rank == 2 && a->tr) {   // storage already is the row-major transpose: plain copy
+        CUDA_TRY(ctx, cudaMemcpyAsync((*out)->data, a->data, (size_t)a->numel * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return TOPS_OK;
+    }
+    if (a->rank == 2) k::transpose2d(lc_of(ctx), (const float*)a->data, (float*)(*out)->data, a->dims[0], a->dims[1]);
+    else k::permute(lc_of(ctx), (const float*)a->data, (float*)(*out)->data, a->rank, a->dims, perm);
+    return check_launch(ctx, "transp");
+}
+extern "C" int tops_eye(tops_ctx* ctx, int64_t n, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    int64_t d[2] = {n, n};
+    TRY(prep_out(ctx, out, TOPS_F32, 2, d));
+    k::eye(lc_of(ctx), (float*)(*out)->data, n);
+    return check_launch(ctx, "eye");
+}
+extern "C" int tops_trace(tops_ctx* ctx, const tops_buf* a, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, a, "tops_trace"));
+    if (a->rank != 2 || a->dims[0] != a->dims[1]) return set_err(ctx, TOPS_ERR_SHAPE, "trace: matrix must be square");
+    TRY(prep_out(ctx, out, TOPS_F32, 0, nullptr));
+    k::trace(lc_of(ctx), (const float*)a->data, a->dims[0], a->dims[0], (float*)(*out)->data);
+    return check_launch(ctx, "trace");
+}
+extern "C" int tops_diag(tops_ctx* ctx, int rank, const tops_buf* v, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, v, "tops_diag"));
+    if (v->rank != 1 || rank < 1 || rank > TOPS_MAX_RANK) return set_err(ctx, TOPS_ERR_SHAPE, "diag: need a vector and 1 <= rank <= %d", TOPS_MAX_RANK);
+    int64_t d[TOPS_MAX_RANK];
+    for (int i = 0; i < rank; ++i) d[i] = v->dims[0];
+    TRY(prep_out(ctx, out, TOPS_F32, rank, d));
+    k::diag_embed(lc_of(ctx), (const float*)v->data, (float*)(*out)->data, v->dims[0], rank);
+    return check_launch(ctx, "diag");
+}
+extern "C" int tops_get_diag(tops_ctx* ctx, const tops_buf* a, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, a, "tops_get_diag"));
+    if (a->rank < 1) return set_err(ctx, TOPS_ERR_SHAPE, "get_diag: rank must be >= 1");
+    for (int i = 1; i < a->rank; ++i) if (a->dims[i] != a->dims[0]) return set_err(ctx, TOPS_ERR_SHAPE, "get_diag: all dimensions must agree");
+    int64_t d[1] = {a->dims[0]};
+    TRY(prep_out(ctx, out, TOPS_F32, 1, d));
+    k::diag_extract(lc_of(ctx), (const float*)a->data, (float*)(*out)->data, a->dims[0], a->rank);   // the diagonal is invariant under transposition
+    return check_launch(ctx, "get_diag");
+}
+
+extern "C" int tops_lift(tops_ctx* ctx, const int32_t* prog, int prog_len, const float* consts, int n_consts,
+                         int n_in, const tops_buf* const* in, int rank, const int64_t* dims, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!prog || prog_len <= 0 || prog_len > 64 || n_consts < 0 || n_consts > 16 || n_in < 0 || n_in > 8)
+        return set_err(ctx, TOPS_ERR_INVALID, "lift: program too long (max 64 ops, 16 constants, 8 inputs)");
+    k::LiftProgram lp{};
+    lp.len = prog_len; lp.n_consts = n_consts;
+    int depth = 0, maxdepth = 0;
+    for (int i = 0; i < prog_len; ++i) {
+        const int op = prog[i] >> 16, arg = prog[i] & 0xffff;
+        lp.code[i] = prog[i];
+        if (op == TOPS_OP_VAR) { if (arg >= n_in) return set_err(ctx, TOPS_ERR_INVALID, "lift: variable %d out of range", arg); ++depth; }
+        else if (op == TOPS_OP_CONST) { if (arg >= n_consts) return set_err(ctx, TOPS_ERR_INVALID, "lift: constant %d out of range", arg); ++depth; }
+        else if (op == TOPS_OP_ADD || op == TOPS_OP_SUB || op == TOPS_OP_MUL || op == TOPS_OP_DIV || op == TOPS_OP_MAX || op == TOPS_OP_MIN || op == TOPS_OP_POW) { if (depth < 2) return set_err(ctx, TOPS_ERR_INVALID, "lift: stack underflow"); --depth; }
+        else if (op >= TOPS_OP_NEG && op <= TOPS_OP_COS) { if (depth < 1) return set_err(ctx, TOPS_ERR_INVALID, "lift: stack underflow"); }
+        else return set_err(ctx, TOPS_ERR_INVALID, "lift: unknown opcode %d", op);
+        if (depth > maxdepth) maxdepth = depth;
+    }
+    if (depth != 1 || maxdepth > 16) return set_err(ctx, TOPS_ERR_INVALID, "lift: program must leave exactly one value (stack depth <= 16)");
+    for (int i = 0; i < n_consts; ++i) lp.consts[i] = consts[i];
+    Tmp tmp;
+    const float* ptrs[8] = {};
+    int64_t n = 1;
+    for (int i = 0; i < rank; ++i) n *= dims[i];
+    for (int j = 0; j < n_in; ++j) {
+        TRY(need_f32(ctx, in[j], "tops_lift"));
+        const tops_buf* s;
+        TRY(contig(ctx, in[j], tmp, &s));
+        if (s->numel != n) return set_err(ctx, TOPS_ERR_SHAPE, "lift: input %d has %lld elements, expected %lld", j, (long long)s->numel, (long long)n);
+        ptrs[j] = (const float*)s->data;
+    }
+    TRY(prep_out(ctx, out, TOPS_F32, rank, dims));
+    k::lift(lc_of(ctx), lp, n_in, ptrs, (float*)(*out)->data, n);
+    return check_launch(ctx, "lift");
+}
+
+// ================================================================================================ class Tensor
+extern "C" int tops_gmul(tops_ctx* ctx, int lM, int lO, int lN, const tops_buf* x, const tops_buf* y, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, x, "tops_gmul")); TRY(need_f32(ctx, y, "tops_gmul"));
+    if (lM < 0 || lO < 0 || lN < 0 || x->rank != lM + lO || y->rank != lO + lN || lM + lN > TOPS_MAX_RANK)
+        return set_err(ctx, TOPS_ERR_SHAPE, "gmul: ranks %d,%d do not match |ms|=%d |os|=%d |ns|=%d", x->rank, y->rank, lM, lO, lN);
+    for (int i = 0; i < lO; ++i)
+        if (x->dims[lM + i] != y->dims[lO - 1 - i]) return set_err(ctx, TOPS_ERR_SHAPE, "gmul: contraction dimension %d differs (%lld vs %lld; y's are reversed)", i, (long long)x->dims[lM + i], (long long)y->dims[lO - 1 - i]);
+    int64_t od[TOPS_MAX_RANK]; int64_t Mx = 1, O = 1, N = 1;
+    for (int i = 0; i < lM; ++i) { od[i] = x->dims[i]; Mx *= x->dims[i]; }
+    for (int i = 0; i < lO; ++i) O *= x->dims[lM + i];
+    for (int i = 0; i < lN; ++i) { od[lM + i] = y->dims[lO + i]; N *= y->dims[lO + i]; }
+    Tmp tmp;
+    // Bring y's leading (reversed) contraction axes into x's order: y'[o.., n..].  |os| <= 1 needs nothing.
+    const tops_buf* yp = y;
+    if (lO >= 2) {
+        const tops_buf* yc;
+        TRY(contig(ctx, y, tmp, &yc));
+        int perm[TOPS_MAX_RANK]; int64_t pd[TOPS_MAX_RANK];
+        for (int i = 0; i < lO; ++i) perm[i] = lO - 1 - i;
+        for (int i = lO; i < lO + lN; ++i) perm[i] = i;
+        for (int i = 0; i < lO + lN; ++i) pd[i] = yc->dims[perm[i]];
+        tops_buf* t = nullptr;
+        TRY(alloc_buf(ctx, TOPS_F32, lO + lN, pd, &t));
+        tmp.keep(t);
+        k::permute(lc_of(ctx), (const float*)yc->data, (float*)t->data, lO + lN, yc->dims, perm);
+        yp = t;
+    }
+    // rank-2 transposed views are consumed directly when they are a plain matrix operand; otherwise materialise
+    const bool x_mat = (lM == 1 && lO == 1), y_mat = (lO == 1 && lN == 1);
+    const tops_buf* xs = x;
+    if (x->tr && !x_mat) TRY(contig(ctx, x, tmp, &xs));
+    if (yp->tr && !y_mat) TRY(contig(ctx, yp, tmp, &yp));
+    TRY(prep_out(ctx, out, TOPS_F32, lM + lN, od));
+    float* o = (float*)(*out)->data;
+    const float* xd = (const float*)xs->data;
+    const float* yd = (const float*)yp->data;
+    if (Mx * N == 0) return TOPS_OK;
+    if (lO == 0) {                                   // outer product / scaling (dispatchBLAS :146-168, naiveGMul for rank >= 3)
+        k::ger(lc_of(ctx), xd, yd, o, Mx, N);
+        return check_launch(ctx, "gmul/outer");
+    }
+    if (Mx == 1 && N == 1) {                         // full contraction -> dot (dispatchDot)
+        k::dot(lc_of(ctx), xd, yd, O, o, ctx->scratch);
+        return check_launch(ctx, "gmul/dot");
+    }
+    if (N == 1) {                                    // matrix-vector (dispatchMV)
+        if (xs->tr) k::gemv(lc_of(ctx), 1.f, xd, 1, yd, 0.f, nullptr, o, Mx, O);
+        else k::gemv(lc_of(ctx), 1.f, xd, 0, yd, 0.f, nullptr, o, Mx, O);
+        return check_launch(ctx, "gmul/mv");
+    }
+    if (Mx == 1) {                                   // vector-matrix (dispatchVM): out[n] = sum_o y'[o,n] x[o]
+        if (yp->tr) k::gemv(lc_of(ctx), 1.f, yd, 0, xd, 0.f, nullptr, o, N, O);      // storage is [N,O] row-major
+        else k::gemv(lc_of(ctx), 1.f, yd, 1, xd, 0.f, nullptr, o, N, O);
+        return check_launch(ctx, "gmul/vm");
+    }
+    GemmCall g{};                                    // everything else: ONE tensor-core GEMM on flat storage
+    g.dtype = 0; g.M = (int)Mx; g.N = (int)N; g.K = (int)O;
+    g.A = xd; g.lda = xs->tr ? Mx : O; g.major_a = xs->tr ? MAJOR_MN : MAJOR_K;
+    g.B = yd; g.ldb = yp->tr ? O : N; g.major_b = yp->tr ? MAJOR_K : MAJOR_MN;
+    g.epi = EPI_STORE; g.alpha = 1.f; g.beta = 0.f; g.out0 = o; g.ld_out0 = N;
+    return run_gemm(ctx, g);
+}
+
+extern "C" int tops_sum_t(tops_ctx* ctx, int n, const tops_buf* const* xs, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (n < 1 || !xs) return set_err(ctx, TOPS_ERR_INVALID, "sum_t: need at least one tensor");
+    Tmp tmp;
+    std::vector<const float*> ptrs;
+    const tops_buf* first = nullptr;
+    for (int j = 0; j < n; ++j) {
+        TRY(need_f32(ctx, xs[j], "tops_sum_t"));
+        const tops_buf* s;
+        TRY(contig(ctx, xs[j], tmp, &s));
+        if (!first) first = s;
+        else if (!same_shape(first, s)) return set_err(ctx, TOPS_ERR_SHAPE, "sum_t: operand %d has a different shape", j);
+        ptrs.push_back((const float*)s->data);
+    }
+    TRY(prep_out(ctx, out, TOPS_F32, first->rank, first->dims));
+    float* o = (float*)(*out)->data;
+    // left fold in order, 8 operands per pass
+    int done = 0;
+    while (done < n) {
+        const float* batch[8]; int nb = 0;
+        if (done > 0) batch[nb++] = o;
+        while (nb < 8 && done < n) batch[nb++] = ptrs[done++];
+        k::add_n(lc_of(ctx), nb, batch, o, first->numel);
+    }
+    return check_launch(ctx, "sum_t");
+}
+extern "C" int tops_sum_rows(tops_ctx* ctx, const tops_buf* x, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, x, "tops_sum_rows"));
+    if (x->rank < 1) return set_err(ctx, TOPS_ERR_SHAPE, "sum_rows: rank must be >= 1");
+    Tmp tmp; const tops_buf* s;
+    TRY(contig(ctx, x, tmp, &s));
+    const int64_t rows = s->dims[0], cols = rows ? s->numel / rows : 0;
+    TRY(prep_out(ctx, out, TOPS_F32, s->rank - 1, s->dims + 1));
+    if (rows == 0) { k::fill(lc_of(ctx), (float*)(*out)->data, (*out)->numel, 0.f); return check_launch(ctx, "sum_rows"); }
+    float* ws = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&ws, sizeof(float) * 64 * (size_t)(cols > 0 ? cols : 1), ctx->stream));
+    k::col_sums(lc_of(ctx), (const float*)s->data, rows, cols, (float*)(*out)->data, ws);
+    cudaFreeAsync(ws, ctx->stream);
+    return check_launch(ctx, "sum_rows");
+}
+extern "C" int tops_broadcast_rows(tops_ctx* ctx, int64_t n, const tops_buf* row, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, row, "tops_broadcast_rows"));
+    if (row->rank + 1 > TOPS_MAX_RANK || n < 0) return set_err(ctx, TOPS_ERR_SHAPE, "broadcast_rows: bad shape");
+    Tmp tmp; const tops_buf* s;
+    TRY(contig(ctx, row, tmp, &s));
+    int64_t d[TOPS_MAX_RANK]; d[0] = n;
+    for (int i = 0; i < s->rank; ++i) d[i + 1] = s->dims[i];
+    TRY(prep_out(ctx, out, TOPS_F32, s->rank + 1, d));
+    k::broadcast_rows(lc_of(ctx), (const float*)s->data, (float*)(*out)->data, n, s->numel);
+    return check_launch(ctx, "broadcast_rows");
+}
+extern "C" int tops_map_rows_softmax(tops_ctx* ctx, const tops_buf* x, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(need_f32(ctx, x, "tops_map_rows_softmax"));
+    if (x->rank != 2) return set_err(ctx, TOPS_ERR_SHAPE, "map_rows_softmax: need a [rows, cols] matrix");
+    Tmp tmp; const tops_buf* s;
+    TRY(contig(ctx, x, tmp, &s));
+    TRY(prep_out(ctx, out, TOPS_F32, 2, s->dims));
+    k::softmax_rows(lc_of(ctx), (const float*)s->data, (float*)(*out)->data, s->dims[0], s->dims[1]);
+    return check_launch(ctx, "softmax");
+}
+
+// ================================================================================================ fused batched hot path
+namespace {
+
+struct LayerShapes { int64_t B, i, o; int dtype; };
+
+int layer_shapes(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops_buf* b, LayerShapes* s) {
+    if (!X || !W) return set_err(ctx, TOPS_ERR_INVALID, "fflayer: NULL tensor");
+    if (X->tr || W->tr) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "fflayer: transposed views are not accepted");
+    if (X->rank != 2 || W->rank != 2 || X->dims[1] != W->dims[1]) return set_err(ctx, TOPS_ERR_SHAPE, "fflayer: X[B,i] W[o,i] expected (FeedForward.hs:209-212)");
+    if (b && (b->rank != 1 || b->dims[0] != W->dims[0] || b->dtype != TOPS_F32)) return set_err(ctx, TOPS_ERR_SHAPE, "fflayer: b[o] (fp32) expected");
+    if (X->dtype != W->dtype) return set_err(ctx, TOPS_ERR_SHAPE, "fflayer: X and W must have the same dtype");
+    s->B = X->dims[0]; s->i = X->dims[1]; s->o = W->dims[0]; s->dtype = X->dtype;
+    return TOPS_OK;
+}
+
+// A = act(X W^T + b)  [optionally also dZ = dA ⊙ act'(A)]  — one GEMM, everything else in its epilogue
+int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, const float* b, int act, int epi,
+             void* A, const void* aux, void* out1, float* loss) {
+    GemmCall g{};
+    g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.o; g.K = (int)s.i;
+    g.A = X; g.lda = s.i; g.major_a = MAJOR_K;
+    g.B = W; g.ldb = s.i; g.major_b = MAJOR_K;
+    g.epi = epi; g.act = act; g.alpha = 1.f; g.bias = b;
+    g.out0 = A; g.ld_out0 = s.o; g.out1 = out1; g.ld_out1 = s.o; g.aux0 = aux; g.ld_aux0 = s.o; g.loss = loss;
+    g.io_bf16 = g.dtype;
+    return run_gemm(ctx, g);
+}
+// dX = dZ W  (optionally ⊙ act'(A_prev))
+int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, void* dX, int epi, int act, const void* Aprev) {
+    GemmCall g{};
+    g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.i; g.K = (int)s.o;
+    g.A = dZ; g.lda = s.o; g.major_a = MAJOR_K;
+    g.B = W; g.ldb = s.i; g.major_b = MAJOR_MN;
+    g.epi = epi; g.act = act; g.alpha = 1.f;
+    g.out0 = dX; g.ld_out0 = s.i; g.aux0 = Aprev; g.ld_aux0 = s.i;
+    g.io_bf16 = g.dtype;
+    return run_gemm(ctx, g);
+}
+// dW = dZ^T Xin   (split-K over the batch, fp32 atomics into a zeroed output), db = column sums of dZ
+int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, float* dW, float* db) {
+    GemmCall g{};
+    g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.o; g.N = (int)s.i; g.K = (int)s.B;
+    g.A = dZ; g.lda = s.o; g.major_a = MAJOR_MN;
+    g.B = Xin; g.ldb = s.i; g.major_b = MAJOR_MN;
+    g.epi = EPI_ATOMIC; g.alpha = 1.f; g.out0 = dW; g.ld_out0 = s.i;
+    TRY(run_gemm(ctx, g));
+    if (db) {
+        float* ws = nullptr;
+        CUDA_TRY(ctx, cudaMallocAsync((void**)&ws, sizeof(float) * 64 * (size_t)s.o, ctx->stream));
+        if (s.dtype == TOPS_BF16) k::col_sums_bf16(lc_of(ctx), dZ, s.B, s.o, db, ws);
+        else k::col_sums(lc_of(ctx), (const float*)dZ, s.B, s.o, db, ws);
+        cudaFreeAsync(ws, ctx->stream);
+        TRY(check_launch(ctx, "col_sums"));
+    }
+    return TOPS_OK;
+}
+
+int check_act(tops_ctx* ctx, int act) {
+    if (act != TOPS_ACT_ID && act != TOPS_ACT_LOGISTIC) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "fflayer: activation %d is not fusable here (use tops_mlp_* for softmax)", act);
+    return TOPS_OK;
+}
+
+}  // namespace
+
+extern "C" int tops_fflayer_fwd(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act, tops_buf** A) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    LayerShapes s; TRY(layer_shapes(ctx, X, W, b, &s)); TRY(check_act(ctx, act));
+    int64_t d[2] = {s.B, s.o};
+    TRY(prep_out(ctx, A, s.dtype, 2, d));
+    return fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT, (*A)->data, nullptr, nullptr, nullptr);
+}
+
+extern "C" int tops_fflayer_fwd_grad(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act,
+                                     const tops_buf* dA, tops_buf** A, tops_buf** dX, tops_buf** dW, tops_buf** db) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    LayerShapes s; TRY(layer_shapes(ctx, X, W, b, &s)); TRY(check_act(ctx, act));
+    if (!dA || dA->rank != 2 || dA->dims[0] != s.B || dA->dims[1] != s.o || dA->dtype != s.dtype || dA->tr) return set_err(ctx, TOPS_ERR_SHAPE, "fflayer: dA[B,o] expected");
+    int64_t dAo[2] = {s.B, s.o}, dXs[2] = {s.B, s.i}, dWs[2] = {s.o, s.i}, dbs[1] = {s.o};
+    TRY(prep_out(ctx, A, s.dtype, 2, dAo));
+    if (dX) TRY(prep_out(ctx, dX, s.dtype, 2, dXs));
+    TRY(prep_out(ctx, dW, TOPS_F32, 2, dWs));
+    if (db) TRY(prep_out(ctx, db, TOPS_F32, 1, dbs));
+    Tmp tmp; tops_buf* dZ = nullptr;
+    TRY(alloc_buf(ctx, s.dtype, 2, dAo, &dZ)); tmp.keep(dZ);
+    TRY(fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, (*A)->data, dA->data, dZ->data, nullptr));
+    TRY(dw_db(ctx, s, dZ->data, X->data, (float*)(*dW)->data, db ? (float*)(*db)->data : nullptr));
+    if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
+    return TOPS_OK;
+}
+
+extern "C" int tops_fflayer_grad(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act,
+                                 const tops_buf* dA, const tops_buf* A_saved, tops_buf** dX, tops_buf** dW, tops_buf** db) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!A_saved) {   // gradTOp' semantics: the forward is recomputed inside the gradient (Types.hs:155)
+        tops_buf* A = nullptr;
+        int r = tops_fflayer_fwd_grad(ctx, X, W, b, act, dA, &A, dX, dW, db);
+        if (A) release_buf(A);
+        return r;
+    }
+    LayerShapes s; TRY(layer_shapes(ctx, X, W, b, &s)); TRY(check_act(ctx, act));
+    if (s.dtype != TOPS_F32) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "fflayer_grad with a saved activation is fp32 only");
+    if (!dA || dA->rank != 2 || dA->dims[0] != s.B || dA->dims[1] != s.o || !same_shape(dA, A_saved) || dA->tr || A_saved->tr) return set_err(ctx, TOPS_ERR_SHAPE, "fflayer: dA[B,o], A[B,o] expected");
+    int64_t dAo[2] = {s.B, s.o}, dXs[2] = {s.B, s.i}, dWs[2] = {s.o, s.i}, dbs[1] = {s.o};
+    if (dX) TRY(prep_out(ctx, dX, TOPS_F32, 2, dXs));
+    TRY(prep_out(ctx, dW, TOPS_F32, 2, dWs));
+    if (db) TRY(prep_out(ctx, db, TOPS_F32, 1, dbs));
+    Tmp tmp; tops_buf* dZ = nullptr;
+    TRY(alloc_buf(ctx, TOPS_F32, 2, dAo, &dZ)); tmp.keep(dZ);
+    k::dact_mul(lc_of(ctx), act, (const float*)dA->data, (const float*)A_saved->data, (float*)dZ->data, dZ->numel);
+    TRY(check_launch(ctx, "dact_mul"));
+    TRY(dw_db(ctx, s, dZ->data, X->data, (float*)(*dW)->data, db ? (float*)(*db)->data : nullptr));
+    if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
+    return TOPS_OK;
+}
+
+namespace {
+
+int mlp_check(tops_ctx* ctx, int n, const tops_buf* const* W, const tops_buf* const* b, const int* acts, const tops_buf* X) {
+    if (n < 1 || !W || !b || !acts || !X) return set_err(ctx, TOPS_ERR_INVALID, "mlp: NULL argument");
+    if (X->rank != 2 || X->dtype != TOPS_F32 || X->tr) return set_err(ctx, TOPS_ERR_SHAPE, "mlp: X[B,i] fp32 expected");
+    int64_t in = X->dims[1];
+    for (int l = 0; l < n; ++l) {
+        if (!W[l] || !b[l] || W[l]->dtype != TOPS_F32 || b[l]->dtype != TOPS_F32 || W[l]->tr || W[l]->rank != 2 || b[l]->rank != 1 || W[l]->dims[1] != in || b[l]->dims[0] != W[l]->dims[0])
+            return set_err(ctx, TOPS_ERR_SHAPE, "mlp: layer %d: W[o,i] b[o] do not chain (i=%lld)", l, (long long)in);
+        if (acts[l] < TOPS_ACT_ID || acts[l] > TOPS_ACT_SOFTMAX) return set_err(ctx, TOPS_ERR_INVALID, "mlp: unknown activation %d", acts[l]);
+        in = W[l]->dims[0];
+    }
+    return TOPS_OK;
+}
+
+// one forward layer: returns Z (only for softmax, else NULL) and A
+int mlp_layer_fwd(tops_ctx* ctx, const tops_buf* in, const tops_buf* W, const tops_buf* b, int act, Tmp& tmp, tops_buf** Zout, tops_buf* A) {
+    LayerShapes s{in->dims[0], in->dims[1], W->dims[0], TOPS_F32};
+    *Zout = nullptr;
+    if (act == TOPS_ACT_SOFTMAX) {
+        int64_t d[2] = {s.B, s.o};
+        tops_buf* Z = nullptr;
+        TRY(alloc_buf(ctx, TOPS_F32, 2, d, &Z)); tmp.keep(Z);
+        TRY(fwd_gemm(ctx, s, in->data, W->data, (const float*)b->data, ACT_ID, EPI_BIAS_ACT, Z->data, nullptr, nullptr, nullptr));
+        if (A) { k::softmax_rows(lc_of(ctx), (const float*)Z->data, (float*)A->data, s.B, s.o); TRY(check_launch(ctx, "softmax")); }
+        *Zout = Z;
+        return TOPS_OK;
+    }
+    return fwd_gemm(ctx, s, in->data, W->data, (const float*)b->data, act, EPI_BIAS_ACT, A->data, nullptr, nullptr, nullptr);
+}
+
+}  // namespace
+
+extern "C" int tops_mlp_fwd(tops_ctx* ctx, int n, const tops_buf* const* W, const tops_buf* const* b, const int* acts, const tops_buf* X, tops_buf** A_out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(mlp_check(ctx, n, W, b, acts, X));
+    Tmp tmp;
+    const tops_buf* cur = X;
+    for (int l = 0; l < n; ++l) {
+        int64_t d[2] = {X->dims[0], W[l]->dims[0]};
+        tops_buf* A = nullptr;
+        if (l == n - 1) { TRY(prep_out(ctx, A_out, TOPS_F32, 2, d)); A = *A_out; }
+        else { TRY(alloc_buf(ctx, TOPS_F32, 2, d, &A)); tmp.keep(A); }
+        tops_buf* Z;
+        TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Z, A));
+        cur = A;
+    }
+    return TOPS_OK;
+}
+
+extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W, const tops_buf* const* b, const int* acts, int loss,
+                                 const tops_buf* X, const tops_buf* Y, tops_buf** A_out, tops_buf** loss_sum, tops_buf** dX,
+                                 tops_buf** dW, tops_buf** db) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(mlp_check(ctx, n, W, b, acts, X));
+    if (loss != TOPS_LOSS_SQUARED_ERROR && loss != TOPS_LOSS_CROSS_ENTROPY) return set_err(ctx, TOPS_ERR_INVALID, "mlp: unknown loss %d", loss);
+    const int64_t B = X->dims[0], o_last = W[n - 1]->dims[0];
+    if (!Y || Y->dtype != TOPS_F32 || Y->rank != 2 || Y->dims[0] != B || Y->dims[1] != o_last || Y->tr) return set_err(ctx, TOPS_ERR_SHAPE, "mlp: Y[B,o] fp32 expected");
+    if (!dW || !db || !A_out || !loss_sum) return set_err(ctx, TOPS_ERR_INVALID, "mlp: NULL output slot");
+    Tmp tmp;
+    std::vector<const tops_buf*> acts_in(n);     // input of layer l
+    std::vector<tops_buf*> Zs(n, nullptr);
+    TRY(prep_out(ctx, loss_sum, TOPS_F32, 0, nullptr));
+    float* lossp = (float*)(*loss_sum)->data;
+    CUDA_TRY(ctx, cudaMemsetAsync(lossp, 0, 4, ctx->stream));
+    // ---- forward; the last layer's epilogue also produces the loss and dZ when the pairing allows
+    const tops_buf* cur = X;
+    tops_buf* dZ = nullptr;
+    for (int l = 0; l < n; ++l) {
+        acts_in[l] = cur;
+        int64_t d[2] = {B, W[l]->dims[0]};
+        tops_buf* A = nullptr;
+        const bool last = (l == n - 1);
+        if (last) { TRY(prep_out(ctx, A_out, TOPS_F32, 2, d)); A = *A_out; }
+        else { TRY(alloc_buf(ctx, TOPS_F32, 2, d, &A)); tmp.keep(A); }
+        if (last) { TRY(alloc_buf(ctx, TOPS_F32, 2, d, &dZ)); tmp.keep(dZ); }
+        if (last && acts[l] != TOPS_ACT_SOFTMAX && loss == TOPS_LOSS_SQUARED_ERROR) {
+            LayerShapes s{B, cur->dims[1], d[1], TOPS_F32};
+            TRY(fwd_gemm(ctx, s, cur->data, W[l]->data, (const float*)b[l]->data, acts[l], EPI_BIAS_ACT_SE, A->data, Y->data, dZ->data, lossp));
+        } else if (last && acts[l] == TOPS_ACT_SOFTMAX && loss == TOPS_LOSS_CROSS_ENTROPY) {
+            TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], nullptr));
+            k::softmax_ce_rows(lc_of(ctx), (const float*)Zs[l]->data, (const float*)Y->data, (float*)A->data, (float*)dZ->data, lossp, B, d[1]);
+            TRY(check_launch(ctx, "softmax_ce"));
+        } else {
+            TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], A));
+            if (last) {   // generic head: loss VJP on activations, then the activation's VJP
+                tops_buf* dA = nullptr;
+                TRY(alloc_buf(ctx, TOPS_F32, 2, d, &dA)); tmp.keep(dA);
+                k::loss_vjp(lc_of(ctx), loss, (const float*)A->data, (const float*)Y->data, (float*)dA->data, lossp, A->numel);
+                if (acts[l] == TOPS_ACT_SOFTMAX) k::softmax_vjp_rows(lc_of(ctx), (const float*)Zs[l]->data, (const float*)dA->data, (float*)dZ->data, B, d[1]);
+                else k::dact_mul(lc_of(ctx), acts[l], (const float*)dA->data, (const float*)A->data, (float*)dZ->data, A->numel);
+                TRY(check_launch(ctx, "loss head"));
+            }
+        }
+        cur = A;
+    }
+    // ---- reverse sweep: dW_l = dZ_l^T in_l, db_l = Σ dZ_l, dZ_{l-1} = (dZ_l W_l) ⊙ act'(A_{l-1}) fused in the GEMM epilogue
+    for (int l = n - 1; l >= 0; --l) {
+        LayerShapes s{B, W[l]->dims[1], W[l]->dims[0], TOPS_F32};
+        int64_t dWs[2] = {s.o, s.i}, dbs[1] = {s.o};
+        TRY(prep_out(ctx, &dW[l], TOPS_F32, 2, dWs));
+        TRY(prep_out(ctx, &db[l], TOPS_F32, 1, dbs));
+        TRY(dw_db(ctx, s, dZ->data, acts_in[l]->data, (float*)dW[l]->data, (float*)db[l]->data));
+        if (l > 0) {
+            int64_t d[2] = {B, s.i};
+            tops_buf* dZp = nullptr;
+            TRY(alloc_buf(ctx, TOPS_F32, 2, d, &dZp)); tmp.keep(dZp);
+            if (acts[l - 1] == TOPS_ACT_SOFTMAX) {
+                tops_buf* dAp = nullptr;
+                TRY(alloc_buf(ctx, TOPS_F32, 2, d, &dAp)); tmp.keep(dAp);
+                TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, dAp->data, EPI_STORE, ACT_ID, nullptr));
+                k::softmax_vjp_rows(lc_of(ctx), (const float*)Zs[l - 1]->data, (const float*)dAp->data, (float*)dZp->data, B, s.i);
+                TRY(check_launch(ctx, "softmax_vjp"));
+            } else {
+                TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, dZp->data, EPI_MUL_DACT, acts[l - 1], acts_in[l]->data));
+            }
+            dZ = dZp;
+        } else if (dX) {
+            int64_t d[2] = {B, s.i};
+            TRY(prep_out(ctx, dX, TOPS_F32, 2, d));
+            TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
+        }
+    }
+    return TOPS_OK;
+}
+
+extern "C" int tops_sgd_step(tops_ctx* ctx, int n, const tops_buf* const* params, const tops_buf* const* grads, double rate, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (n < 0 || !params || !grads || !out) return set_err(ctx, TOPS_ERR_INVALID, "sgd_step: NULL argument");
+    for (int j = 0; j < n; ++j) {
+        TRY(need_f32(ctx, params[j], "tops_sgd_step")); TRY(need_f32(ctx, grads[j], "tops_sgd_step"));
+        if (params[j]->tr || grads[j]->tr || !same_shape(params[j], grads[j])) return set_err(ctx, TOPS_ERR_SHAPE, "sgd_step: parameter %d and its gradient differ in shape", j);
+        TRY(prep_out(ctx, &out[j], TOPS_F32, params[j]->rank, params[j]->dims));
+        k::sgd(lc_of(ctx), (const float*)params[j]->data, (const float*)grads[j]->data, (float)rate, (float*)out[j]->data, params[j]->numel);
+    }
+    return check_launch(ctx, "sgd_step");
+}

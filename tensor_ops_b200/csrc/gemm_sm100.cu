@@ -1,0 +1,160 @@
+// Instantiations, TMA tensor-map construction and launch logic for the tcgen05 GEMM (gemm_sm100.cuh).
+#include "gemm_sm100.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdio.h>
+
+#include <mutex>
+
+#include "gemm_sm100.cuh"
+
+namespace tops {
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_encode_once;
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    });
+    return g_encode;
+}
+
+// 2-D row-major tensor [outer, inner] with leading dimension ld (elements); box = box_inner x box_outer, 128B swizzle.
+bool make_map(CUtensorMap* m, int dtype, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, bool atom32) {
+    auto enc = get_encode();
+    if (!enc) return false;
+    const size_t es = dtype == 1 ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return false;
+    if (((size_t)ld * es) % 16 != 0) return false;
+    if (inner <= 0 || outer <= 0) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
+cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+    using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES>;
+    auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES>;
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    return cudaGetLastError();
+}
+
+template <typename T, int MA, int MB>
+cudaError_t launch_major(int bn, int passes, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        if (passes == 3) {
+            if (bn == 128) return launch_one<T, MA, MB, 128, 3, 3>(ta, tb, p, grid, st);
+            return launch_one<T, MA, MB, 256, 2, 3>(ta, tb, p, grid, st);
+        }
+    }
+    if (bn == 128) return launch_one<T, MA, MB, 128, 6, 1>(ta, tb, p, grid, st);
+    return launch_one<T, MA, MB, 256, 4, 1>(ta, tb, p, grid, st);
+}
+
+template <typename T>
+cudaError_t launch_dtype(int ma, int mb, int bn, int passes, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+    if (ma == MAJOR_K && mb == MAJOR_K) return launch_major<T, MAJOR_K, MAJOR_K>(bn, passes, ta, tb, p, grid, st);
+    if (ma == MAJOR_K && mb == MAJOR_MN) return launch_major<T, MAJOR_K, MAJOR_MN>(bn, passes, ta, tb, p, grid, st);
+    if (ma == MAJOR_MN && mb == MAJOR_K) return launch_major<T, MAJOR_MN, MAJOR_K>(bn, passes, ta, tb, p, grid, st);
+    return launch_major<T, MAJOR_MN, MAJOR_MN>(bn, passes, ta, tb, p, grid, st);
+}
+
+}  // namespace
+
+int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watchdog_dev, int num_sms, char* err, size_t errlen) {
+    auto fail = [&](int code, const char* msg) {
+        if (err && errlen) snprintf(err, errlen, "%s", msg);
+        return code;
+    };
+    if (c.M <= 0 || c.N <= 0 || c.K <= 0) return fail(-1, "gemm: empty problem");
+    if (c.passes == 3 && c.dtype != 0) return fail(-1, "gemm: 3-pass split needs fp32 operands");
+    const int es = c.dtype == 1 ? 2 : 4;
+    const int kb_elems = 128 / es;
+    int bn = c.block_n;
+    if (bn == 0) bn = (c.N <= 128) ? 128 : 256;
+    if (bn != 128 && bn != 256) return fail(-1, "gemm: block_n must be 128 or 256");
+
+    CUtensorMap ta, tb;
+    bool ok;
+    if (c.major_a == MAJOR_K) ok = make_map(&ta, c.dtype, c.A, c.K, c.M, c.lda, kb_elems, 128, false);
+    else ok = make_map(&ta, c.dtype, c.A, c.M, c.K, c.lda, kb_elems, kb_elems, c.dtype == 0);
+    if (!ok) return fail(-1, "gemm: operand A not expressible as a TMA tensor map (alignment/stride)");
+    if (c.major_b == MAJOR_K) ok = make_map(&tb, c.dtype, c.B, c.K, c.N, c.ldb, kb_elems, bn, false);
+    else ok = make_map(&tb, c.dtype, c.B, c.N, c.K, c.ldb, kb_elems, kb_elems, c.dtype == 0);
+    if (!ok) return fail(-1, "gemm: operand B not expressible as a TMA tensor map (alignment/stride)");
+
+    GemmParams p{};
+    p.M = c.M; p.N = c.N; p.K = c.K;
+    p.num_m_tiles = (c.M + 127) / 128;
+    p.num_n_tiles = (c.N + bn - 1) / bn;
+    p.num_k_blocks = (c.K + kb_elems - 1) / kb_elems;
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int ctas = c.max_ctas > 0 ? c.max_ctas : num_sms;
+    int split = c.split_k;
+    if (c.epi != EPI_ATOMIC) split = 1;
+    else if (split <= 0) {
+        split = 1;
+        if (tiles < ctas) {
+            split = (2 * ctas) / tiles;
+            const int max_split = p.num_k_blocks / 8 > 0 ? p.num_k_blocks / 8 : 1;   // keep >= 8 k-blocks per work item
+            if (split > max_split) split = max_split;
+            if (split < 1) split = 1;
+        }
+    }
+    if (c.epi == EPI_ATOMIC && c.passes == 3) {
+        // TMEM accumulation truncates (error grows linearly with the chain length, measured ~2e-8 per MMA):
+        // keep each fp32-grade chain <= 1024 K-elements and let the fp32 atomics (round-to-nearest) do the rest.
+        const int min_split = (p.num_k_blocks + 31) / 32;
+        if (split < min_split) split = min_split;
+    }
+    if (split > p.num_k_blocks) split = p.num_k_blocks;
+    p.kb_per_split = (p.num_k_blocks + split - 1) / split;
+    p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    p.epi = c.epi; p.act = c.act; p.alpha = c.alpha; p.beta = c.beta;
+    p.out0 = c.out0; p.ld_out0 = c.ld_out0;
+    p.out1 = c.out1; p.ld_out1 = c.ld_out1;
+    p.aux0 = c.aux0; p.ld_aux0 = c.ld_aux0;
+    p.bias = c.bias; p.loss = c.loss;
+    p.io_bf16 = c.io_bf16;
+    p.watchdog = watchdog_dev;
+    auto vec_ok = [&](const void* ptr, long long ld) {
+        if (!ptr) return true;
+        const int oes = c.io_bf16 ? 2 : 4;
+        return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((size_t)ld * oes) % 16 == 0;
+    };
+    p.vec_ok = vec_ok(c.out0, c.ld_out0) && vec_ok(c.out1, c.ld_out1) && vec_ok(c.aux0, c.ld_aux0);
+    if (c.epi == EPI_ATOMIC) p.vec_ok = (reinterpret_cast<uintptr_t>(c.out0) & 15) == 0 && (c.ld_out0 % 4) == 0;
+
+    const int total = tiles * p.split_k;
+    const int grid = total < ctas ? total : ctas;
+    cudaError_t e;
+    if (c.dtype == 1) e = launch_dtype<__nv_bfloat16>(c.major_a, c.major_b, bn, 1, ta, tb, p, grid, stream);
+    else e = launch_dtype<float>(c.major_a, c.major_b, bn, c.passes == 3 ? 3 : 1, ta, tb, p, grid, stream);
+    if (e != cudaSuccess) {
+        if (err && errlen) snprintf(err, errlen, "gemm launch: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+}  // namespace tops

@@ -1,0 +1,415 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
+//
+// Operands are fp32 (consumed as TF32, one pass, or as a 3-pass hi/lo split that recovers fp32 accuracy)
+// or bf16; accumulation is fp32 in TMEM.  Either operand may be K-major (row = MN index, K contiguous) or
+// MN-major (row = K index, MN contiguous) so that the three GEMMs of an ffLayer forward + VJP
+//   Z  = X  W^T        (A = X  K-major,  B = W  K-major)
+//   dX = dZ W          (A = dZ K-major,  B = W  MN-major)
+//   dW = dZ^T X        (A = dZ MN-major, B = X  MN-major, split-K)
+// run on the tensor cores without any transposed copy in HBM.
+//
+// Roles (one CTA per SM, persistent over work items):
+//   warp 0      TMA producer      global -> 128B-swizzled smem ring (mbarrier full[])
+//   warp 1      MMA issuer        one thread issues tcgen05.mma into TMEM, commits to empty[] / tmem_full[]
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue          tcgen05.ld -> registers -> fused bias / logistic / VJP math -> global
+//   warps 8-11  (3-pass only) splitter: lo = x - trunc_tf32(x) into a second tile (ready[]); the raw tile serves as hi
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include "umma.cuh"
+
+namespace tops {
+
+enum : int { MAJOR_K = 0, MAJOR_MN = 1 };
+enum : int {
+    EPI_STORE = 0,        // out0 = alpha*acc (+ beta*aux0)
+    EPI_ATOMIC = 1,       // out0 += alpha*acc                (split-K partials, red.global.add)
+    EPI_BIAS_ACT = 2,     // out0 = act(acc + bias[n])
+    EPI_BIAS_ACT_DZ = 3,  // a = act(acc + bias[n]); out0 = a; out1 = aux0 * act'(a)           (aux0 = dA)
+    EPI_MUL_DACT = 4,     // out0 = acc * act'(aux0)                                          (aux0 = A of the previous layer)
+    EPI_BIAS_ACT_SE = 5,  // a = act(acc+bias); d = aux0 - a; loss += d*d; out0 = a; out1 = -2 d act'(a)   (aux0 = target)
+};
+enum : int { ACT_ID = 0, ACT_LOGISTIC = 1 };
+
+struct GemmParams {
+    int M, N, K;
+    int num_m_tiles, num_n_tiles;
+    int num_k_blocks;   // ceil(K / KB_ELEMS)
+    int split_k;        // number of K partitions (>= 1)
+    int kb_per_split;   // k-blocks per partition
+    int epi, act;
+    float alpha, beta;
+    void* out0; long long ld_out0;
+    void* out1; long long ld_out1;
+    const void* aux0; long long ld_aux0;
+    const float* bias;
+    float* loss;              // scalar accumulator (EPI_BIAS_ACT_SE)
+    int io_bf16;              // out0/out1/aux0 are bf16 (bf16 pipelines); 0 = fp32
+    int vec_ok;               // 16-byte vector access legal for out0/out1/aux0
+    unsigned int* watchdog;   // mapped host memory, 2 words
+};
+
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
+struct GemmCfg {
+    static constexpr int BM = 128;
+    static constexpr int KB_ELEMS = 128 / (int)sizeof(T);   // K elements per stage (one 128B swizzle row)
+    static constexpr int UMMA_K = 32 / (int)sizeof(T);      // K elements per tcgen05.mma
+    static constexpr int KSTEPS = KB_ELEMS / UMMA_K;        // = 4
+    static constexpr int A_BYTES = BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = RAW_BYTES * (PASSES == 3 ? 2 : 1);
+    static constexpr int NUM_THREADS = PASSES == 3 ? 384 : 256;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+    static_assert(PASSES == 1 || (PASSES == 3 && sizeof(T) == 4), "3-pass split is an fp32 technique");
+    static_assert(BN == 128 || BN == 256, "BN");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ float act_apply(int act, float z) {
+    if (act == ACT_LOGISTIC) return __fdividef(1.0f, 1.0f + __expf(-z));   // NeuralNet.hs:42-44
+    return z;
+}
+__device__ __forceinline__ float act_deriv_from_out(int act, float a) {
+    if (act == ACT_LOGISTIC) return a * (1.0f - a);                        // NeuralNet.hs:46-50
+    return 1.0f;
+}
+
+template <bool BF16>
+__device__ __forceinline__ void ld_row32(const void* base, long long ld, int row, int col, int N, bool vec, float (&x)[32]) {
+    if constexpr (BF16) {
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + (long long)row * ld + col;
+        if (vec && col + 32 <= N) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + q);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 f = __bfloat1622float2(h[e]);
+                    x[q * 8 + e * 2] = f.x; x[q * 8 + e * 2 + 1] = f.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = (col + e < N) ? __bfloat162float(p[e]) : 0.f;
+        }
+    } else {
+        const float* p = reinterpret_cast<const float*>(base) + (long long)row * ld + col;
+        if (vec && col + 32 <= N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 f = __ldg(reinterpret_cast<const float4*>(p) + q);
+                x[q * 4] = f.x; x[q * 4 + 1] = f.y; x[q * 4 + 2] = f.z; x[q * 4 + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = (col + e < N) ? p[e] : 0.f;
+        }
+    }
+}
+
+template <bool BF16>
+__device__ __forceinline__ void st_row32(void* base, long long ld, int row, int col, int N, bool vec, const float (&x)[32]) {
+    if constexpr (BF16) {
+        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + (long long)row * ld + col;
+        if (vec && col + 32 <= N) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(x[q * 8 + e * 2], x[q * 8 + e * 2 + 1]);
+                reinterpret_cast<uint4*>(p)[q] = u;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) if (col + e < N) p[e] = __float2bfloat16_rn(x[e]);
+        }
+    } else {
+        float* p = reinterpret_cast<float*>(base) + (long long)row * ld + col;
+        if (vec && col + 32 <= N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(p)[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) if (col + e < N) p[e] = x[e];
+        }
+    }
+}
+
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
+__global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES>::NUM_THREADS), 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES>;
+    constexpr bool kBF16 = sizeof(T) == 2;
+    constexpr int BM = Cfg::BM;
+    constexpr int KB = Cfg::KB_ELEMS;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]  TMA landed
+    uint64_t* empty_bar = bars + STAGES;             // [STAGES]  MMAs reading the stage retired
+    uint64_t* ready_bar = bars + 2 * STAGES;         // [STAGES]  hi/lo split done (3-pass)
+    uint64_t* tmem_full = bars + 3 * STAGES;         // [2]
+    uint64_t* tmem_empty = bars + 3 * STAGES + 2;    // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    volatile unsigned int* wd = p.watchdog;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&ready_bar[s], 128);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tmem_full[a], 1);
+            ptx::mbar_init(&tmem_empty[a], 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int total_work = num_tiles * p.split_k;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int tile = w % num_tiles, split = w / num_tiles;
+                const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1, wd, 0x100 + s);
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::RAW_BYTES);
+                    uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    if constexpr (MA == MAJOR_K) {
+                        ptx::tma_load_2d(sa, &tmA, &full_bar[s], kb * KB, m0);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < BM / KB; ++r)
+                            ptx::tma_load_2d(sa + r * (KB * 128), &tmA, &full_bar[s], m0 + r * KB, kb * KB);
+                    }
+                    if constexpr (MB == MAJOR_K) {
+                        ptx::tma_load_2d(sb, &tmB, &full_bar[s], kb * KB, n0);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < BN / KB; ++r)
+                            ptx::tma_load_2d(sb + r * (KB * 128), &tmB, &full_bar[s], n0 + r * KB, kb * KB);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc(kBF16 ? 1u : 2u, MA == MAJOR_MN, MB == MAJOR_MN, BM, BN);
+            // byte advance of the descriptor start address per UMMA_K step, and the LBO/SBO of each layout
+            constexpr uint32_t a_step = (MA == MAJOR_K) ? 32u : (uint32_t)Cfg::UMMA_K * 128u;
+            constexpr uint32_t b_step = (MB == MAJOR_K) ? 32u : (uint32_t)Cfg::UMMA_K * 128u;
+            constexpr uint32_t a_lbo = (MA == MAJOR_K) ? 16u : (uint32_t)KB * 128u;
+            constexpr uint32_t b_lbo = (MB == MAJOR_K) ? 16u : (uint32_t)KB * 128u;
+            // MN-major 32-bit operands must use the 32B-atom flavour of the 128B swizzle (4-row atoms, SBO = 512)
+            constexpr uint32_t a_lt = (MA == MAJOR_MN && !kBF16) ? 1u : 2u, b_lt = (MB == MAJOR_MN && !kBF16) ? 1u : 2u;
+            constexpr uint32_t a_sbo = a_lt == 1u ? 512u : 1024u, b_sbo = b_lt == 1u ? 512u : 1024u;
+            int s = 0; uint32_t ph = 0; int it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+                const int split = w / num_tiles;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+                const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, wd, 0x200 + acc);
+                ptx::tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t first = 1;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(PASSES == 3 ? &ready_bar[s] : &full_bar[s], ph, wd, 0x300 + s);
+                    ptx::tcgen05_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int pass = 0; pass < PASSES; ++pass) {
+                        // pass 0: A_hi*B_hi   pass 1: A_lo*B_hi   pass 2: A_hi*B_lo
+                        const uint32_t pa = sa + (pass == 1 ? Cfg::RAW_BYTES : 0);
+                        const uint32_t pb = sb + (pass == 2 ? Cfg::RAW_BYTES : 0);
+#pragma unroll
+                        for (int j = 0; j < Cfg::KSTEPS; ++j) {
+                            const uint64_t ad = ptx::make_smem_desc_sw128(pa + j * a_step, a_lbo, a_sbo, a_lt);
+                            const uint64_t bd = ptx::make_smem_desc_sw128(pb + j * b_step, b_lbo, b_sbo, b_lt);
+                            if constexpr (kBF16) ptx::umma_f16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                            else ptx::umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                    }
+                    ptx::umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                ptx::umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================================================== epilogue
+        const int q = warp & 3;   // TMEM lane quarter this warp may read
+        const bool vec = p.vec_ok != 0;
+        int it = 0;
+        float loss_acc = 0.f;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+            const int tile = w % num_tiles;
+            const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+            const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+            ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
+            ptx::tcgen05_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32b_x32(t_row + c * 32, raw);
+                ptx::tmem_ld_wait();
+                const int col = n0 + c * 32;
+                if (row < p.M && col < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
+                    switch (p.epi) {
+                        case EPI_STORE: {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] *= p.alpha;
+                            if (p.aux0 != nullptr) {
+                                float x[32];
+                                ld_row32<kBF16>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+#pragma unroll
+                                for (int e = 0; e < 32; ++e) v[e] = fmaf(p.beta, x[e], v[e]);
+                            }
+                            if (p.io_bf16) st_row32<true>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+                            else st_row32<false>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+                        } break;
+                        case EPI_ATOMIC: {
+                            float* o = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out0 + col;
+                            if (vec && col + 32 <= p.N) {
+#pragma unroll
+                                for (int g = 0; g < 8; ++g)
+                                    ptx::red_add_v4(o + g * 4, p.alpha * v[g * 4], p.alpha * v[g * 4 + 1], p.alpha * v[g * 4 + 2], p.alpha * v[g * 4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 32; ++e) if (col + e < p.N) atomicAdd(o + e, p.alpha * v[e]);
+                            }
+                        } break;
+                        case EPI_BIAS_ACT:
+                        case EPI_BIAS_ACT_DZ:
+                        case EPI_BIAS_ACT_SE: {
+                            if (p.bias != nullptr) {
+#pragma unroll
+                                for (int e = 0; e < 32; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
+                            }
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = act_apply(p.act, v[e]);
+                            if (p.io_bf16) st_row32<true>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+                            else st_row32<false>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+                            if (p.epi != EPI_BIAS_ACT) {
+                                float x[32];
+                                if (p.io_bf16) ld_row32<true>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+                                else ld_row32<false>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+                                if (p.epi == EPI_BIAS_ACT_DZ) {
+#pragma unroll
+                                    for (int e = 0; e < 32; ++e) v[e] = x[e] * act_deriv_from_out(p.act, v[e]);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 32; ++e) {
+                                        const float d = (col + e < p.N) ? x[e] - v[e] : 0.f;   // squaredError: NeuralNet.hs:61-68
+                                        loss_acc = fmaf(d, d, loss_acc);
+                                        v[e] = -2.0f * d * act_deriv_from_out(p.act, v[e]);
+                                    }
+                                }
+                                if (p.io_bf16) st_row32<true>(p.out1, p.ld_out1, row, col, p.N, vec, v);
+                                else st_row32<false>(p.out1, p.ld_out1, row, col, p.N, vec, v);
+                            }
+                        } break;
+                        case EPI_MUL_DACT: {
+                            float x[32];
+                            if (p.io_bf16) ld_row32<true>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+                            else ld_row32<false>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] *= act_deriv_from_out(p.act, x[e]);
+                            if (p.io_bf16) st_row32<true>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+                            else st_row32<false>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+                        } break;
+                        default: break;
+                    }
+                }
+            }
+            ptx::tcgen05_fence_before();
+            ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+            if (lane == 0) atomicAdd(p.loss, loss_acc);
+        }
+    } else if (PASSES == 3 && warp >= 8) {
+        // ===================================================== hi/lo splitter (3xTF32)
+        const int t = threadIdx.x - 256;   // 0..127
+        int s = 0; uint32_t ph = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int split = w / num_tiles;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                ptx::mbar_wait(&full_bar[s], ph, wd, 0x500 + s);
+                float4* hi = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + Cfg::RAW_BYTES);
+#pragma unroll 4
+                for (int i = t; i < Cfg::RAW_BYTES / 16; i += 128) {
+                    // kind::tf32 TRUNCATES fp32 operands (measured: tools/gemm_probe, ref_mode=1), so the raw tile already
+                    // acts as hi = trunc_tf32(x); only lo = x - hi (exact in fp32) has to be materialised.
+                    const float4 x = hi[i];
+                    float4 l;
+                    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                    l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                    l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                    lo[i] = l;
+                }
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(&ready_bar[s]);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace tops

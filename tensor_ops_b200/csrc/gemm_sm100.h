@@ -1,0 +1,32 @@
+// Host-side interface of the tcgen05 GEMM engine (internal to libtops_b200; the public C ABI is include/tops_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace tops {
+
+struct GemmCall {
+    int dtype;      // 0 = fp32 operands (TF32 tensor cores), 1 = bf16 operands
+    int passes;     // 1 = single TF32/bf16 pass, 3 = 3xTF32 hi/lo split (fp32-grade accuracy)
+    int M, N, K;
+    const void* A; long long lda; int major_a;   // 0: A stored [M,K] (K contiguous), 1: stored [K,M]
+    const void* B; long long ldb; int major_b;   // 0: B stored [N,K] (K contiguous), 1: stored [K,N]
+    int epi, act;
+    float alpha, beta;
+    void* out0; long long ld_out0;
+    void* out1; long long ld_out1;
+    const void* aux0; long long ld_aux0;
+    const float* bias;
+    float* loss;
+    int io_bf16;
+    int split_k;    // 0 = choose automatically (only EPI_ATOMIC may split)
+    int block_n;    // 0 = choose automatically, else 128 or 256
+    int max_ctas;   // 0 = number of SMs
+};
+
+// returns 0 on success; -1 if the problem cannot be expressed as TMA tensor maps (caller uses the SIMT kernel);
+// >0 cudaError_t on launch failure.  `err` receives a message.
+int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watchdog_dev, int num_sms, char* err, size_t errlen);
+
+}  // namespace tops

@@ -1,0 +1,672 @@
+// Bandwidth-bound kernels of libtops_b200: generation, elementwise (incl. the `liftT` bytecode interpreter),
+// deterministic two-stage reductions, BLAS-2, layout permutation, the softmax / loss heads, and a CUDA-core GEMM
+// that honours the same operand/epilogue contract as the tcgen05 engine.  Grid-stride loops sized in multiples
+// of the SM count, 128-bit accesses where alignment allows, warp-shuffle reductions.
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+
+#include "gemm_sm100.cuh"   // epilogue enums, act_apply / act_deriv_from_out
+
+namespace tops {
+namespace k {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(const LaunchCtx& lc, int64_t work_items, int per_block = kThreads, int waves = 8) {
+    int64_t b = (work_items + per_block - 1) / per_block;
+    int64_t cap = (int64_t)lc.num_sms * waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+inline void count(const LaunchCtx& lc) { if (lc.launches) ++*lc.launches; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {   // sh: >= 32 floats; result valid in thread 0
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) {
+        r = (l < (blockDim.x >> 5)) ? sh[l] : 0.f;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f); }
+
+__global__ void k_fill(float* p, int64_t n, float v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_bf16(__nv_bfloat16* p, int64_t n, float v) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = b;
+}
+template <bool NORMAL>
+__global__ void k_rand(float* p, int64_t n, float a, float b, uint64_t seed) {
+    const int64_t n4 = (n + 3) / 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 r = philox(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        float v[4];
+        if (NORMAL) {   // Box-Muller, mean a, sd b
+            const float r0 = sqrtf(-2.0f * logf(u01(r.x))), r1 = sqrtf(-2.0f * logf(u01(r.z)));
+            float s0, c0, s1, c1;
+            sincospif(2.0f * u01(r.y), &s0, &c0);
+            sincospif(2.0f * u01(r.w), &s1, &c1);
+            v[0] = a + b * r0 * c0; v[1] = a + b * r0 * s0; v[2] = a + b * r1 * c1; v[3] = a + b * r1 * s1;
+        } else {        // uniform [a, b)
+            v[0] = a + (b - a) * u01(r.x); v[1] = a + (b - a) * u01(r.y); v[2] = a + (b - a) * u01(r.z); v[3] = a + (b - a) * u01(r.w);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (i * 4 + e < n) p[i * 4 + e] = v[e];
+    }
+}
+__global__ void k_cast_f2b(const float* s, __nv_bfloat16* d, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void k_cast_b2f(const __nv_bfloat16* s, float* d, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = __bfloat162float(s[i]);
+}
+__global__ void k_eye(float* p, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (i / n == i % n) ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------ elementwise, float4 body + scalar tail
+template <typename F>
+__global__ void k_map1(const float* __restrict__ x, float* __restrict__ out, int64_t n, bool vec, F f) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = vec ? n / 4 : 0;
+    for (int64_t i = tid; i < n4; i += nth) {
+        float4 a = reinterpret_cast<const float4*>(x)[i];
+        reinterpret_cast<float4*>(out)[i] = make_float4(f(a.x), f(a.y), f(a.z), f(a.w));
+    }
+    for (int64_t i = n4 * 4 + tid; i < n; i += nth) out[i] = f(x[i]);
+}
+template <typename F>
+__global__ void k_map2(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t n, bool vec, F f) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = vec ? n / 4 : 0;
+    for (int64_t i = tid; i < n4; i += nth) {
+        float4 a = reinterpret_cast<const float4*>(x)[i], b = reinterpret_cast<const float4*>(y)[i];
+        reinterpret_cast<float4*>(out)[i] = make_float4(f(a.x, b.x), f(a.y, b.y), f(a.z, b.z), f(a.w, b.w));
+    }
+    for (int64_t i = n4 * 4 + tid; i < n; i += nth) out[i] = f(x[i], y[i]);
+}
+
+struct InPtrs { const float* p[8]; };
+
+__global__ void k_add_n(InPtrs in, int n_in, float* __restrict__ out, int64_t n, bool vec) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = vec ? n / 4 : 0;
+    for (int64_t i = tid; i < n4; i += nth) {
+        float4 acc = reinterpret_cast<const float4*>(in.p[0])[i];
+        for (int j = 1; j < n_in; ++j) {
+            float4 b = reinterpret_cast<const float4*>(in.p[j])[i];
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = acc;
+    }
+    for (int64_t i = n4 * 4 + tid; i < n; i += nth) {
+        float acc = in.p[0][i];
+        for (int j = 1; j < n_in; ++j) acc += in.p[j][i];
+        out[i] = acc;
+    }
+}
+
+__global__ void k_bias_act(int act, const float* __restrict__ Z, const float* __restrict__ bias, float* __restrict__ A, int64_t rows, int64_t cols) {
+    const int64_t n = rows * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        A[i] = act_apply(act, Z[i] + (bias ? bias[i % cols] : 0.f));
+}
+
+// ------------------------------------------------------------------ liftT interpreter: 4 elements per thread
+__device__ __forceinline__ float lift_unary(int op, float a) {
+    switch (op) {
+        case 6: return -a;
+        case 7: return __expf(a);
+        case 8: return __logf(a);
+        case 9: return __fdividef(1.0f, a);
+        case 10: return sqrtf(a);
+        case 11: return tanhf(a);
+        case 12: return fabsf(a);
+        case 13: return (a > 0.f) - (a < 0.f);
+        case 17: return __fdividef(1.0f, 1.0f + __expf(-a));
+        case 18: return sinf(a);
+        case 19: return cosf(a);
+    }
+    return a;
+}
+__device__ __forceinline__ float lift_binary(int op, float a, float b) {
+    switch (op) {
+        case 2: return a + b;
+        case 3: return a - b;
+        case 4: return a * b;
+        case 5: return a / b;
+        case 14: return fmaxf(a, b);
+        case 15: return fminf(a, b);
+        case 16: return powf(a, b);
+    }
+    return a;
+}
+__global__ void k_lift(LiftProgram prog, InPtrs in, int n_in, float* __restrict__ out, int64_t n, bool vec) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t ngroups = (n + 3) / 4;
+    for (int64_t g = tid; g < ngroups; g += nth) {
+        const int64_t base = g * 4;
+        const int cnt = (int)min((int64_t)4, n - base);
+        float x[8][4];
+        for (int j = 0; j < n_in; ++j) {
+            if (vec && cnt == 4) {
+                float4 v = reinterpret_cast<const float4*>(in.p[j])[g];
+                x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w;
+            } else {
+                for (int e = 0; e < 4; ++e) x[j][e] = e < cnt ? in.p[j][base + e] : 1.0f;
+            }
+        }
+        float st[16][4];
+        int sp = 0;
+        for (int pc = 0; pc < prog.len; ++pc) {
+            const int op = prog.code[pc] >> 16, arg = prog.code[pc] & 0xffff;
+            if (op == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) st[sp][e] = x[arg][e];
+                ++sp;
+            } else if (op == 1) {
+                const float c = prog.consts[arg];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) st[sp][e] = c;
+                ++sp;
+            } else if (op == 2 || op == 3 || op == 4 || op == 5 || op == 14 || op == 15 || op == 16) {
+                --sp;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) st[sp - 1][e] = lift_binary(op, st[sp - 1][e], st[sp][e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) st[sp - 1][e] = lift_unary(op, st[sp - 1][e]);
+            }
+        }
+        if (vec && cnt == 4) reinterpret_cast<float4*>(out)[g] = make_float4(st[0][0], st[0][1], st[0][2], st[0][3]);
+        else for (int e = 0; e < cnt; ++e) out[base + e] = st[0][e];
+    }
+}
+
+// ------------------------------------------------------------------ reductions
+template <bool DOT>
+__global__ void k_reduce_partial(const float* __restrict__ x, const float* __restrict__ y, int64_t n, float* __restrict__ partial) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += DOT ? x[i] * y[i] : x[i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void k_reduce_final(const float* __restrict__ partial, int np, float* __restrict__ out) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acc += partial[i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) *out = acc;
+}
+__global__ void k_trace(const float* __restrict__ a, int64_t n, int64_t ld, float* __restrict__ out) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += a[i * ld + i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) *out = acc;
+}
+
+// column sums / transposed gemv: partial[chunk][c] = sum_{r in chunk} w[r] * x[r, c]
+template <typename TIn>
+__global__ void k_colsum_partial(const TIn* __restrict__ x, const float* __restrict__ w, int64_t rows, int64_t cols, int64_t rows_per_chunk, float* __restrict__ partial) {
+    __shared__ float sh[8][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c0 = (int64_t)blockIdx.x * 128;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = min(rows, r0 + rows_per_chunk);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+        const float wr = w ? w[r] : 1.0f;
+        const TIn* row = x + r * cols + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t c = c0 + lane + 32 * j;
+            if (c < cols) acc[j] = fmaf(wr, (float)row[lane + 32 * j], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sh[warp][lane + 32 * j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += sh[wv][threadIdx.x];
+        const int64_t c = c0 + threadIdx.x;
+        if (c < cols) partial[(int64_t)blockIdx.y * cols + c] = s;
+    }
+}
+__global__ void k_colsum_final(const float* __restrict__ partial, int chunks, int64_t cols, float alpha, float beta, const float* __restrict__ y, float* __restrict__ out) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols; c += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k2 = 0; k2 < chunks; ++k2) s += partial[(int64_t)k2 * cols + c];
+        out[c] = alpha * s + (y ? beta * y[c] : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------ BLAS-2 / layout
+__global__ void k_ger(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t n, int64_t m) {
+    const int64_t tot = n * m;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) out[i] = x[i / m] * y[i % m];
+}
+// one warp per output row; A row-major [n,m]
+__global__ void k_gemv_rows(float alpha, const float* __restrict__ a, const float* __restrict__ x, float beta, const float* __restrict__ y, float* __restrict__ out, int64_t n, int64_t m, bool vec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        const float* row = a + r * m;
+        float acc = 0.f;
+        if (vec) {
+            for (int64_t c = lane * 4; c < m; c += 128) {
+                const float4 av = *reinterpret_cast<const float4*>(row + c), xv = *reinterpret_cast<const float4*>(x + c);
+                acc += av.x * xv.x + av.y * xv.y + av.z * xv.z + av.w * xv.w;
+            }
+        } else {
+            for (int64_t c = lane; c < m; c += 32) acc = fmaf(row[c], x[c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[r] = alpha * acc + (y ? beta * y[r] : 0.f);
+    }
+}
+__global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int64_t cols) {
+    __shared__ float t[32][33];
+    const int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t r = by + j, c = bx + threadIdx.x;
+        if (r < rows && c < cols) t[j][threadIdx.x] = in[r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int64_t c = bx + j, r = by + threadIdx.x;
+        if (r < rows && c < cols) out[c * rows + r] = t[threadIdx.x][j];
+    }
+}
+struct PermArgs { int rank; int64_t out_dims[8]; int64_t in_strides_for_out[8]; };
+__global__ void k_permute(const float* __restrict__ in, float* __restrict__ out, PermArgs pa, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t rem = i, off = 0;
+        for (int a = pa.rank - 1; a >= 0; --a) {
+            const int64_t idx = rem % pa.out_dims[a];
+            rem /= pa.out_dims[a];
+            off += idx * pa.in_strides_for_out[a];
+        }
+        out[i] = in[off];
+    }
+}
+__global__ void k_broadcast_rows(const float* __restrict__ row, float* __restrict__ out, int64_t n, int64_t m) {
+    const int64_t tot = n * m;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) out[i] = row[i % m];
+}
+__global__ void k_diag_embed(const float* __restrict__ v, float* __restrict__ out, int64_t n, int64_t step) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i * step] = v[i];
+}
+__global__ void k_diag_extract(const float* __restrict__ a, float* __restrict__ out, int64_t n, int64_t step) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i * step];
+}
+
+// ------------------------------------------------------------------ softmax / loss heads: one warp per row (sample)
+// mode 0: A = softmax(Z)    mode 1: dZ = softmax-VJP(Z, dA)    mode 2: fused softmax + crossEntropy (A, loss, dZ)
+template <int MODE>
+__global__ void k_softmax_rows(const float* __restrict__ Z, const float* __restrict__ aux, float* __restrict__ A, float* __restrict__ dZ, float* __restrict__ loss, int64_t rows, int64_t cols) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float loss_acc = 0.f;
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        const float* z = Z + r * cols;
+        float se = 0.f;
+        for (int64_t c = lane; c < cols; c += 32) se += __expf(z[c]);        // map exp >>> sumRows (no max-subtraction: NeuralNet.hs:52-59)
+        se = warp_sum(se);
+        const float rinv = 1.0f / se;                                          // map recip
+        if (MODE == 0) {
+            for (int64_t c = lane; c < cols; c += 32) A[r * cols + c] = __expf(z[c]) * rinv;   // outer LZ (LS LZ): scalar * vector
+        } else {
+            // dA: given (MODE 1) or from crossEntropy: dA = -(y / a)   (NeuralNet.hs:71-77 VJP)
+            float s = 0.f;
+            for (int64_t c = lane; c < cols; c += 32) {
+                const float e = __expf(z[c]);
+                float d;
+                if (MODE == 2) {
+                    const float a = e * rinv, yv = aux[r * cols + c];
+                    A[r * cols + c] = a;
+                    loss_acc -= __logf(a) * yv;
+                    d = -(yv / a);
+                } else d = aux[r * cols + c];
+                s += d * e;
+            }
+            s = warp_sum(s);                                                   // VJP of outer wrt the scalar: dot(dA, E)
+            const float ds = -(rinv * rinv) * s;                               // VJP of recip, broadcast by sumRows' VJP
+            for (int64_t c = lane; c < cols; c += 32) {
+                const float e = __expf(z[c]);
+                float d;
+                if (MODE == 2) { const float a = e * rinv; d = -(aux[r * cols + c] / a); } else d = aux[r * cols + c];
+                dZ[r * cols + c] = (ds + d * rinv) * e;                        // duplicate's sumT [d1,d2], then map exp VJP
+            }
+        }
+    }
+    if (MODE == 2 && loss) {
+        loss_acc = warp_sum(loss_acc);
+        if (lane == 0) atomicAdd(loss, loss_acc);
+    }
+}
+__global__ void k_loss_vjp(int loss, const float* __restrict__ A, const float* __restrict__ Y, float* __restrict__ dA, float* __restrict__ out, int64_t n) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = A[i], y = Y[i];
+        if (loss == 1) { const float d = y - a; acc = fmaf(d, d, acc); dA[i] = -2.0f * d; }
+        else { acc -= __logf(a) * y; dA[i] = -(y / a); }
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0 && out) atomicAdd(out, acc);
+}
+
+// ------------------------------------------------------------------ CUDA-core GEMM (64x64x16 tiles, 4x4 per thread)
+__device__ __forceinline__ void epi_elem(const GemmParams& p, int row, int col, float acc, float& loss_acc) {
+    float* o0 = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out0 + col;
+    switch (p.epi) {
+        case EPI_STORE: {
+            float v = p.alpha * acc;
+            if (p.aux0) v = fmaf(p.beta, reinterpret_cast<const float*>(p.aux0)[(long long)row * p.ld_aux0 + col], v);
+            *o0 = v;
+        } break;
+        case EPI_ATOMIC: atomicAdd(o0, p.alpha * acc); break;
+        case EPI_BIAS_ACT:
+        case EPI_BIAS_ACT_DZ:
+        case EPI_BIAS_ACT_SE: {
+            const float a = act_apply(p.act, acc + (p.bias ? p.bias[col] : 0.f));
+            *o0 = a;
+            if (p.epi != EPI_BIAS_ACT) {
+                const float x = reinterpret_cast<const float*>(p.aux0)[(long long)row * p.ld_aux0 + col];
+                float* o1 = reinterpret_cast<float*>(p.out1) + (long long)row * p.ld_out1 + col;
+                if (p.epi == EPI_BIAS_ACT_DZ) *o1 = x * act_deriv_from_out(p.act, a);
+                else { const float d = x - a; loss_acc = fmaf(d, d, loss_acc); *o1 = -2.0f * d * act_deriv_from_out(p.act, a); }
+            }
+        } break;
+        case EPI_MUL_DACT: {
+            const float x = reinterpret_cast<const float*>(p.aux0)[(long long)row * p.ld_aux0 + col];
+            *o0 = acc * act_deriv_from_out(p.act, x);
+        } break;
+        default: break;
+    }
+}
+
+template <int MA, int MB>
+__global__ void __launch_bounds__(256) k_gemm_simt(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, GemmParams p) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int kchunk = (p.K + gridDim.z - 1) / gridDim.z;
+    const int k_begin = blockIdx.z * kchunk, k_end = min(p.K, k_begin + kchunk);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            int mm, kk;
+            if (MA == MAJOR_K) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            float v = 0.f;
+            if (gm < p.M && gk < k_end) v = MA == MAJOR_K ? A[(long long)gm * lda + gk] : A[(long long)gk * lda + gm];
+            As[kk][mm] = v;
+        }
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            int nn, kk;
+            if (MB == MAJOR_K) { kk = i & 15; nn = i >> 4; } else { nn = i & 63; kk = i >> 6; }
+            const int gn = n0 + nn, gk = k0 + kk;
+            float v = 0.f;
+            if (gn < p.N && gk < k_end) v = MB == MAJOR_K ? B[(long long)gn * ldb + gk] : B[(long long)gk * ldb + gn];
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float loss_acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = m0 + ty * 4 + i, col = n0 + tx * 4 + j;
+            if (row < p.M && col < p.N) epi_elem(p, row, col, acc[i][j], loss_acc);
+        }
+    if (p.epi == EPI_BIAS_ACT_SE && p.loss) {
+        __shared__ float sh[32];
+        loss_acc = block_sum(loss_acc, sh);
+        if (threadIdx.x == 0) atomicAdd(p.loss, loss_acc);
+    }
+}
+
+}  // namespace
+
+// ====================================================================== launch wrappers
+void fill(const LaunchCtx& lc, float* p, int64_t n, float v) { if (n <= 0) return; k_fill<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(p, n, v); count(lc); }
+void fill_bf16(const LaunchCtx& lc, void* p, int64_t n, float v) { if (n <= 0) return; k_fill_bf16<<<grid_for(lc, n), kThreads, 0, lc.stream>>>((__nv_bfloat16*)p, n, v); count(lc); }
+void rand_normal(const LaunchCtx& lc, float* p, int64_t n, float mean, float sd, uint64_t seed) { if (n <= 0) return; k_rand<true><<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(p, n, mean, sd, seed); count(lc); }
+void rand_uniform(const LaunchCtx& lc, float* p, int64_t n, float lo, float hi, uint64_t seed) { if (n <= 0) return; k_rand<false><<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(p, n, lo, hi, seed); count(lc); }
+void cast_f32_bf16(const LaunchCtx& lc, const float* s, void* d, int64_t n) { if (n <= 0) return; k_cast_f2b<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(s, (__nv_bfloat16*)d, n); count(lc); }
+void cast_bf16_f32(const LaunchCtx& lc, const void* s, float* d, int64_t n) { if (n <= 0) return; k_cast_b2f<<<grid_for(lc, n), kThreads, 0, lc.stream>>>((const __nv_bfloat16*)s, d, n); count(lc); }
+void eye(const LaunchCtx& lc, float* p, int64_t n) { if (n <= 0) return; k_eye<<<grid_for(lc, n * n), kThreads, 0, lc.stream>>>(p, n); count(lc); }
+
+void axpy(const LaunchCtx& lc, float alpha, const float* x, const float* y, float* out, int64_t n) {
+    if (n <= 0) return;
+    const int g = grid_for(lc, (n + 3) / 4);
+    if (y) {
+        const bool vec = aligned16(x) && aligned16(y) && aligned16(out);
+        k_map2<<<g, kThreads, 0, lc.stream>>>(x, y, out, n, vec, [alpha] __device__(float a, float b) { return fmaf(alpha, a, b); });
+    } else {
+        const bool vec = aligned16(x) && aligned16(out);
+        k_map1<<<g, kThreads, 0, lc.stream>>>(x, out, n, vec, [alpha] __device__(float a) { return alpha * a; });
+    }
+    count(lc);
+}
+void add_n(const LaunchCtx& lc, int n_in, const float* const* xs, float* out, int64_t n) {
+    if (n <= 0) return;
+    InPtrs in{};
+    bool vec = aligned16(out);
+    for (int j = 0; j < n_in; ++j) { in.p[j] = xs[j]; vec = vec && aligned16(xs[j]); }
+    k_add_n<<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(in, n_in, out, n, vec);
+    count(lc);
+}
+void sgd(const LaunchCtx& lc, const float* p, const float* g, float rate, float* out, int64_t n) {
+    if (n <= 0) return;
+    const bool vec = aligned16(p) && aligned16(g) && aligned16(out);
+    k_map2<<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(p, g, out, n, vec, [rate] __device__(float a, float b) { return a - rate * b; });   // FeedForward.hs:141-147
+    count(lc);
+}
+void dact_mul(const LaunchCtx& lc, int act, const float* dA, const float* A, float* dZ, int64_t n) {
+    if (n <= 0) return;
+    const bool vec = aligned16(dA) && aligned16(A) && aligned16(dZ);
+    k_map2<<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(dA, A, dZ, n, vec, [act] __device__(float d, float a) { return d * act_deriv_from_out(act, a); });
+    count(lc);
+}
+void bias_act(const LaunchCtx& lc, int act, const float* Z, const float* bias, float* A, int64_t rows, int64_t cols) {
+    if (rows * cols <= 0) return;
+    k_bias_act<<<grid_for(lc, rows * cols), kThreads, 0, lc.stream>>>(act, Z, bias, A, rows, cols);
+    count(lc);
+}
+void lift(const LaunchCtx& lc, const LiftProgram& prog, int n_in, const float* const* in, float* out, int64_t n) {
+    if (n <= 0) return;
+    InPtrs ip{};
+    bool vec = aligned16(out);
+    for (int j = 0; j < n_in; ++j) { ip.p[j] = in[j]; vec = vec && aligned16(in[j]); }
+    k_lift<<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(prog, ip, n_in, out, n, vec);
+    count(lc);
+}
+
+void sum_all(const LaunchCtx& lc, const float* x, int64_t n, float* out, float* ws) {
+    const int g = grid_for(lc, n > 0 ? n : 1, kThreads, 4);
+    k_reduce_partial<false><<<g, kThreads, 0, lc.stream>>>(x, nullptr, n, ws); count(lc);
+    k_reduce_final<<<1, kThreads, 0, lc.stream>>>(ws, g, out); count(lc);
+}
+void dot(const LaunchCtx& lc, const float* x, const float* y, int64_t n, float* out, float* ws) {
+    const int g = grid_for(lc, n > 0 ? n : 1, kThreads, 4);
+    k_reduce_partial<true><<<g, kThreads, 0, lc.stream>>>(x, y, n, ws); count(lc);
+    k_reduce_final<<<1, kThreads, 0, lc.stream>>>(ws, g, out); count(lc);
+}
+void trace(const LaunchCtx& lc, const float* a, int64_t n, int64_t ld, float* out) { k_trace<<<1, kThreads, 0, lc.stream>>>(a, n, ld, out); count(lc); }
+
+static int colsum_chunks(const LaunchCtx& lc, int64_t rows, int64_t cols) {
+    const int64_t cb = (cols + 127) / 128;
+    int64_t chunks = (4 * (int64_t)lc.num_sms + cb - 1) / cb;
+    if (chunks > 64) chunks = 64;
+    if (chunks > (rows + 7) / 8) chunks = (rows + 7) / 8;
+    if (chunks < 1) chunks = 1;
+    return (int)chunks;
+}
+void col_sums(const LaunchCtx& lc, const float* x, int64_t rows, int64_t cols, float* out, float* ws) {
+    if (cols <= 0) return;
+    const int chunks = colsum_chunks(lc, rows, cols);
+    const int64_t rpc = (rows + chunks - 1) / chunks;
+    dim3 g((unsigned)((cols + 127) / 128), (unsigned)chunks);
+    k_colsum_partial<float><<<g, 256, 0, lc.stream>>>(x, nullptr, rows, cols, rpc, ws); count(lc);
+    k_colsum_final<<<grid_for(lc, cols), kThreads, 0, lc.stream>>>(ws, chunks, cols, 1.0f, 0.f, nullptr, out); count(lc);
+}
+void col_sums_bf16(const LaunchCtx& lc, const void* x, int64_t rows, int64_t cols, float* out, float* ws) {
+    if (cols <= 0) return;
+    const int chunks = colsum_chunks(lc, rows, cols);
+    const int64_t rpc = (rows + chunks - 1) / chunks;
+    dim3 g((unsigned)((cols + 127) / 128), (unsigned)chunks);
+    k_colsum_partial<__nv_bfloat16><<<g, 256, 0, lc.stream>>>((const __nv_bfloat16*)x, nullptr, rows, cols, rpc, ws); count(lc);
+    k_colsum_final<<<grid_for(lc, cols), kThreads, 0, lc.stream>>>(ws, chunks, cols, 1.0f, 0.f, nullptr, out); count(lc);
+}
+
+void ger(const LaunchCtx& lc, const float* x, const float* y, float* out, int64_t n, int64_t m) {
+    if (n * m <= 0) return;
+    k_ger<<<grid_for(lc, n * m), kThreads, 0, lc.stream>>>(x, y, out, n, m); count(lc);
+}
+void gemv(const LaunchCtx& lc, float alpha, const float* a, int a_tr, const float* x, float beta, const float* y, float* out, int64_t n, int64_t m) {
+    if (n <= 0) return;
+    if (!a_tr) {
+        const bool vec = aligned16(a) && aligned16(x) && (m % 4 == 0);
+        k_gemv_rows<<<grid_for(lc, n * 32, kThreads, 8), kThreads, 0, lc.stream>>>(alpha, a, x, beta, y, out, n, m, vec);
+        count(lc);
+    } else {
+        // A stored [m, n]: weighted column sums, two-stage; workspace comes from the caller through `out`-sized temp — use a static per-stream scratch
+        // (rows = m, cols = n).  chunks*n floats of scratch are carved from a cudaMallocAsync allocation.
+        const int chunks = colsum_chunks(lc, m, n);
+        const int64_t rpc = (m + chunks - 1) / chunks;
+        float* ws = nullptr;
+        cudaMallocAsync(&ws, sizeof(float) * (size_t)chunks * (size_t)n, lc.stream);
+        dim3 g((unsigned)((n + 127) / 128), (unsigned)chunks);
+        k_colsum_partial<float><<<g, 256, 0, lc.stream>>>(a, x, m, n, rpc, ws); count(lc);
+        k_colsum_final<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(ws, chunks, n, alpha, beta, y, out); count(lc);
+        cudaFreeAsync(ws, lc.stream);
+    }
+}
+void transpose2d(const LaunchCtx& lc, const float* in, float* out, int64_t rows, int64_t cols) {
+    if (rows * cols <= 0) return;
+    dim3 g((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), b(32, 8);
+    k_transpose<<<g, b, 0, lc.stream>>>(in, out, rows, cols); count(lc);
+}
+void permute(const LaunchCtx& lc, const float* in, float* out, int rank, const int64_t* in_dims, const int* perm) {
+    PermArgs pa{};
+    pa.rank = rank;
+    int64_t in_strides[8];
+    int64_t s = 1;
+    for (int a = rank - 1; a >= 0; --a) { in_strides[a] = s; s *= in_dims[a]; }
+    const int64_t n = s;
+    for (int a = 0; a < rank; ++a) { pa.out_dims[a] = in_dims[perm[a]]; pa.in_strides_for_out[a] = in_strides[perm[a]]; }
+    if (n <= 0) return;
+    k_permute<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(in, out, pa, n); count(lc);
+}
+void broadcast_rows(const LaunchCtx& lc, const float* row, float* out, int64_t n, int64_t m) {
+    if (n * m <= 0) return;
+    k_broadcast_rows<<<grid_for(lc, n * m), kThreads, 0, lc.stream>>>(row, out, n, m); count(lc);
+}
+static int64_t diag_step(int64_t n, int rank) { int64_t step = 0, s = 1; for (int a = 0; a < rank; ++a) { step += s; s *= n; } return step; }
+void diag_embed(const LaunchCtx& lc, const float* v, float* out, int64_t n, int rank) {
+    int64_t tot = 1; for (int a = 0; a < rank; ++a) tot *= n;
+    fill(lc, out, tot, 0.f);
+    if (n <= 0) return;
+    k_diag_embed<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(v, out, n, diag_step(n, rank)); count(lc);
+}
+void diag_extract(const LaunchCtx& lc, const float* a, float* out, int64_t n, int rank) {
+    if (n <= 0) return;
+    k_diag_extract<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(a, out, n, diag_step(n, rank)); count(lc);
+}
+
+void softmax_rows(const LaunchCtx& lc, const float* Z, float* A, int64_t rows, int64_t cols) {
+    if (rows * cols <= 0) return;
+    k_softmax_rows<0><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, nullptr, A, nullptr, nullptr, rows, cols); count(lc);
+}
+void softmax_vjp_rows(const LaunchCtx& lc, const float* Z, const float* dA, float* dZ, int64_t rows, int64_t cols) {
+    if (rows * cols <= 0) return;
+    k_softmax_rows<1><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, dA, nullptr, dZ, nullptr, rows, cols); count(lc);
+}
+void softmax_ce_rows(const LaunchCtx& lc, const float* Z, const float* Y, float* A, float* dZ, float* loss, int64_t rows, int64_t cols) {
+    if (rows * cols <= 0) return;
+    k_softmax_rows<2><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, Y, A, dZ, loss, rows, cols); count(lc);
+}
+void loss_vjp(const LaunchCtx& lc, int loss, const float* A, const float* Y, float* dA, float* loss_out, int64_t n) {
+    if (n <= 0) return;
+    k_loss_vjp<<<grid_for(lc, n, kThreads, 4), kThreads, 0, lc.stream>>>(loss, A, Y, dA, loss_out, n); count(lc);
+}
+
+int gemm_simt(const LaunchCtx& lc, const GemmCall& c) {
+    if (c.dtype != 0 || c.io_bf16) return -1;
+    if (c.M <= 0 || c.N <= 0) return 0;
+    GemmParams p{};
+    p.M = c.M; p.N = c.N; p.K = c.K;
+    p.epi = c.epi; p.act = c.act; p.alpha = c.alpha; p.beta = c.beta;
+    p.out0 = c.out0; p.ld_out0 = c.ld_out0; p.out1 = c.out1; p.ld_out1 = c.ld_out1;
+    p.aux0 = c.aux0; p.ld_aux0 = c.ld_aux0; p.bias = c.bias; p.loss = c.loss;
+    const int gx = (c.N + 63) / 64, gy = (c.M + 63) / 64;
+    int gz = 1;
+    if (c.epi == EPI_ATOMIC) {
+        gz = c.split_k > 0 ? c.split_k : (int)((2LL * lc.num_sms + (long long)gx * gy - 1) / ((long long)gx * gy));
+        const int maxz = (c.K + 255) / 256;
+        if (gz > maxz) gz = maxz;
+        if (gz < 1) gz = 1;
+    }
+    dim3 g(gx, gy, gz);
+    const float* A = reinterpret_cast<const float*>(c.A);
+    const float* B = reinterpret_cast<const float*>(c.B);
+    if (c.major_a == MAJOR_K && c.major_b == MAJOR_K) k_gemm_simt<MAJOR_K, MAJOR_K><<<g, 256, 0, lc.stream>>>(A, c.lda, B, c.ldb, p);
+    else if (c.major_a == MAJOR_K) k_gemm_simt<MAJOR_K, MAJOR_MN><<<g, 256, 0, lc.stream>>>(A, c.lda, B, c.ldb, p);
+    else if (c.major_b == MAJOR_K) k_gemm_simt<MAJOR_MN, MAJOR_K><<<g, 256, 0, lc.stream>>>(A, c.lda, B, c.ldb, p);
+    else k_gemm_simt<MAJOR_MN, MAJOR_MN><<<g, 256, 0, lc.stream>>>(A, c.lda, B, c.ldb, p);
+    count(lc);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace k
+}  // namespace tops

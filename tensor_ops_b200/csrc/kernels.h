@@ -1,0 +1,68 @@
+// Launch wrappers for the bandwidth-bound (non tensor-core) kernels of libtops_b200 — internal header.
+// Everything here is fp32 unless noted; all launches go to the given stream and never synchronise.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_sm100.h"
+
+namespace tops {
+namespace k {
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    int num_sms;
+    int64_t* launches;   // incremented once per kernel launch
+};
+
+// ---- generation
+void fill(const LaunchCtx&, float* p, int64_t n, float v);
+void fill_bf16(const LaunchCtx&, void* p, int64_t n, float v);
+void rand_normal(const LaunchCtx&, float* p, int64_t n, float mean, float sd, uint64_t seed);
+void rand_uniform(const LaunchCtx&, float* p, int64_t n, float lo, float hi, uint64_t seed);
+void cast_f32_bf16(const LaunchCtx&, const float* s, void* d, int64_t n);
+void cast_bf16_f32(const LaunchCtx&, const void* s, float* d, int64_t n);
+void eye(const LaunchCtx&, float* p, int64_t n);
+
+// ---- elementwise
+void axpy(const LaunchCtx&, float alpha, const float* x, const float* y /*nullable*/, float* out, int64_t n);
+void add_n(const LaunchCtx&, int n_in, const float* const* xs, float* out, int64_t n);   // left fold, n_in <= 8
+void sgd(const LaunchCtx&, const float* p, const float* g, float rate, float* out, int64_t n);
+void dact_mul(const LaunchCtx&, int act, const float* dA, const float* A, float* dZ, int64_t n);   // dZ = dA * act'(A)
+void bias_act(const LaunchCtx&, int act, const float* Z, const float* bias, float* A, int64_t rows, int64_t cols);
+// lift: postfix program, up to 8 inputs
+struct LiftProgram { int len; int n_consts; int32_t code[64]; float consts[16]; };
+void lift(const LaunchCtx&, const LiftProgram& prog, int n_in, const float* const* in, float* out, int64_t n);
+
+// ---- reductions (deterministic two-stage)
+void sum_all(const LaunchCtx&, const float* x, int64_t n, float* out_scalar, float* workspace /* >= 1024 floats */);
+void dot(const LaunchCtx&, const float* x, const float* y, int64_t n, float* out_scalar, float* workspace);
+void trace(const LaunchCtx&, const float* a, int64_t n, int64_t ld, float* out_scalar);
+void col_sums(const LaunchCtx&, const float* x, int64_t rows, int64_t cols, float* out, float* workspace /* >= 64*cols floats */);
+void col_sums_bf16(const LaunchCtx&, const void* x, int64_t rows, int64_t cols, float* out, float* workspace);
+
+// ---- BLAS-2 / layout
+void ger(const LaunchCtx&, const float* x, const float* y, float* out, int64_t n, int64_t m);
+// out[n] = alpha * sum_m A(n,m) x[m] + beta*y[n];  a_tr = 0: A stored [n,m] row-major, 1: stored [m,n]
+void gemv(const LaunchCtx&, float alpha, const float* a, int a_tr, const float* x, float beta, const float* y, float* out, int64_t n, int64_t m);
+void transpose2d(const LaunchCtx&, const float* in, float* out, int64_t rows, int64_t cols);   // out[c,r] = in[r,c]
+void permute(const LaunchCtx&, const float* in, float* out, int rank, const int64_t* in_dims, const int* perm);   // out axis a = in axis perm[a]
+void broadcast_rows(const LaunchCtx&, const float* row, float* out, int64_t n, int64_t m);
+void diag_embed(const LaunchCtx&, const float* v, float* out, int64_t n, int rank);
+void diag_extract(const LaunchCtx&, const float* a, float* out, int64_t n, int rank);
+
+// ---- losses / softmax (rows = samples)
+void softmax_rows(const LaunchCtx&, const float* Z, float* A, int64_t rows, int64_t cols);   // exp / sum exp, no max-subtraction (NeuralNet.hs:52-59)
+// dZ = VJP of the reference softmax TOp given dA (A not needed: recomputed from Z like the reference's closures)
+void softmax_vjp_rows(const LaunchCtx&, const float* Z, const float* dA, float* dZ, int64_t rows, int64_t cols);
+// fused softmax + crossEntropy head: A = softmax(Z); loss += -sum(log A * Y); dZ = VJP chain of crossEntropy∘softmax
+void softmax_ce_rows(const LaunchCtx&, const float* Z, const float* Y, float* A, float* dZ, float* loss, int64_t rows, int64_t cols);
+// loss VJPs on activations: squaredError dA = -2 (Y - A), loss += sum (Y-A)^2 ; crossEntropy dA = -Y / A, loss += -sum(log A * Y)
+void loss_vjp(const LaunchCtx&, int loss, const float* A, const float* Y, float* dA, float* loss_out, int64_t n);
+
+// ---- CUDA-core GEMM with the same operand/epilogue contract as the tcgen05 engine (fp32 only)
+int gemm_simt(const LaunchCtx&, const GemmCall& c);
+
+}  // namespace k
+}  // namespace tops
