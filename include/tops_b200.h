@@ -69,6 +69,11 @@ int tops_get_precision(tops_ctx* ctx);
 /* number of kernels this library has launched on the context so far (bench.py's gpu_launches) */
 int64_t tops_launch_count(tops_ctx* ctx);
 int tops_device_sm_count(tops_ctx* ctx);
+/* Per-kernel device timing for bench.py's roofline: when enabled, tagged launches (gemm_fwd / gemm_dX / gemm_dW /
+ * col_sums_db / gemm / gmul) are bracketed by CUDA events on the context's stream.  tops_profile_summary synchronises,
+ * writes {"tag": {"launches", "ms", "flops", "bytes"}} as JSON into `json_out` and clears the records. */
+int tops_profile_enable(tops_ctx* ctx, int on);
+int tops_profile_summary(tops_ctx* ctx, char* json_out, size_t cap);
 
 /* ------------------------------------------------------------------ storage
  * replaces: hmatrix Storable Vector/Matrix allocation inside every HMat method (BLAS/HMat.hs:37-39),

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "tops_get_precision": (C.c_int, [c_ctx]),
     "tops_launch_count": (C.c_int64, [c_ctx]),
     "tops_device_sm_count": (C.c_int, [c_ctx]),
+    "tops_profile_enable": (C.c_int, [c_ctx, C.c_int]),
+    "tops_profile_summary": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t]),
     "tops_buf_alloc": (C.c_int, [c_ctx, C.c_int, C.c_int, c_i64p, c_bufp]),
     "tops_buf_wrap": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int, c_i64p, c_bufp]),
     "tops_buf_view": (C.c_int, [c_ctx, c_buf, C.c_int64, C.c_int, c_i64p, c_bufp]),

@@ -29,6 +29,10 @@ struct tops_ctx {
     unsigned int* wd_host = nullptr;
     unsigned int* wd_dev = nullptr;
     float* scratch = nullptr;   // small persistent workspace for reductions (1 MiB)
+    // optional per-kernel timing (tops_profile_*): CUDA events recorded on ctx->stream around tagged launches
+    struct ProfRec { const char* tag; cudaEvent_t e0, e1; double flops, bytes; };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
 };
 
 struct tops_buf {
@@ -72,6 +76,23 @@ int check_launch(tops_ctx* ctx, const char* what) {
     if (e != cudaSuccess) return set_err(ctx, TOPS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return TOPS_OK;
 }
+
+// RAII: brackets the launches issued in its scope with two events when profiling is on (no-op otherwise)
+struct ProfScope {
+    tops_ctx* ctx; bool on = false; tops_ctx::ProfRec r{};
+    ProfScope(tops_ctx* c, const char* tag, double flops, double bytes) : ctx(c) {
+        if (!c->profiling) return;
+        if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { cudaGetLastError(); return; }
+        r.tag = tag ? tag : "untagged"; r.flops = flops; r.bytes = bytes;
+        cudaEventRecord(r.e0, c->stream);
+        on = true;
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(r.e1, ctx->stream);
+        ctx->prof.push_back(r);
+    }
+};
 
 int new_buf(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, void* data, bool owns, tops_buf* parent, tops_buf** out) {
     if (rank < 0 || rank > TOPS_MAX_RANK) return set_err(ctx, TOPS_ERR_INVALID, "rank %d out of range", rank);
@@ -160,6 +181,9 @@ int need_f32(tops_ctx* ctx, const tops_buf* x, const char* what) {
 // ---------------------------------------------------------------------------------------------- GEMM dispatch
 int run_gemm(tops_ctx* ctx, GemmCall c) {
     if (c.M <= 0 || c.N <= 0) return TOPS_OK;
+    const double es_in = c.dtype == 1 ? 2.0 : 4.0, es_out = c.io_bf16 ? 2.0 : 4.0;
+    ProfScope prof_(ctx, c.tag ? c.tag : "gemm", 2.0 * c.M * c.N * (double)(c.K > 0 ? c.K : 0),
+                    es_in * ((double)c.M * c.K + (double)c.N * c.K) + (c.epi == EPI_ATOMIC ? 4.0 : es_out) * (double)c.M * c.N * ((c.out1 ? 1 : 0) + (c.aux0 ? 1 : 0) + 1));
     if (c.epi == EPI_ATOMIC) {
         CUDA_TRY(ctx, cudaMemsetAsync(c.out0, 0, sizeof(float) * (size_t)c.M * (size_t)c.ld_out0, ctx->stream));
     }
@@ -254,6 +278,41 @@ extern "C" int tops_set_precision(tops_ctx* ctx, int p) {
     return TOPS_OK;
 }
 extern "C" int tops_get_precision(tops_ctx* ctx) { return ctx ? ctx->precision : -1; }
+extern "C" int tops_profile_enable(tops_ctx* ctx, int on) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    ctx->profiling = on != 0;
+    return TOPS_OK;
+}
+// Synchronises the stream, aggregates the recorded event pairs per tag and clears them.  JSON:
+//   {"<tag>": {"launches": n, "ms": total, "flops": total, "bytes": total}, ...}
+extern "C" int tops_profile_summary(tops_ctx* ctx, char* out, size_t cap) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!out || cap < 3) return set_err(ctx, TOPS_ERR_INVALID, "tops_profile_summary: NULL/short output buffer");
+    TRY(tops_sync(ctx));
+    struct Agg { std::string tag; int n; double ms, flops, bytes; };
+    std::vector<Agg> aggs;
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.e1);
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+        Agg* a = nullptr;
+        for (auto& x : aggs) if (x.tag == r.tag) a = &x;
+        if (!a) { aggs.push_back(Agg{r.tag, 0, 0, 0, 0}); a = &aggs.back(); }
+        a->n += 1; a->ms += ms; a->flops += r.flops; a->bytes += r.bytes;
+    }
+    ctx->prof.clear();
+    std::string js = "{";
+    for (size_t i = 0; i < aggs.size(); ++i) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %d, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", i ? ", " : "", aggs[i].tag.c_str(), aggs[i].n, aggs[i].ms, aggs[i].flops, aggs[i].bytes);
+        js += buf;
+    }
+    js += "}";
+    if (js.size() + 1 > cap) return set_err(ctx, TOPS_ERR_INVALID, "tops_profile_summary: buffer of %zu bytes too small (%zu needed)", cap, js.size() + 1);
+    memcpy(out, js.c_str(), js.size() + 1);
+    return TOPS_OK;
+}
 extern "C" int64_t tops_launch_count(tops_ctx* ctx) { return ctx ? ctx->launches : -1; }
 extern "C" int tops_device_sm_count(tops_ctx* ctx) { return ctx ? ctx->num_sms : -1; }
 
@@ -410,7 +469,7 @@ extern "C" int tops_gemm(tops_ctx* ctx, double alpha, const tops_buf* a, const t
     g.dtype = 0; g.M = (int)d[0]; g.N = (int)d[1]; g.K = (int)a->dims[1];
     as_operand(a, 1, &g.A, &g.lda, &g.major_a);
     as_operand(b, 0, &g.B, &g.ldb, &g.major_b);
-    g.epi = EPI_STORE; g.alpha = (float)alpha; g.beta = (float)beta;
+    g.epi = EPI_STORE; g.alpha = (float)alpha; g.beta = (float)beta; g.tag = "gemm";
     g.out0 = (*out)->data; g.ld_out0 = d[1];
     if (cs) { g.aux0 = cs->data; g.ld_aux0 = d[1]; }
     return run_gemm(ctx, g);
@@ -606,7 +665,7 @@ extern "C" int tops_gmul(tops_ctx* ctx, int lM, int lO, int lN, const tops_buf* 
     g.dtype = 0; g.M = (int)Mx; g.N = (int)N; g.K = (int)O;
     g.A = xd; g.lda = xs->tr ? Mx : O; g.major_a = xs->tr ? MAJOR_MN : MAJOR_K;
     g.B = yd; g.ldb = yp->tr ? O : N; g.major_b = yp->tr ? MAJOR_K : MAJOR_MN;
-    g.epi = EPI_STORE; g.alpha = 1.f; g.beta = 0.f; g.out0 = o; g.ld_out0 = N;
+    g.epi = EPI_STORE; g.alpha = 1.f; g.beta = 0.f; g.out0 = o; g.ld_out0 = N; g.tag = "gmul";
     return run_gemm(ctx, g);
 }
 
@@ -696,7 +755,7 @@ int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, 
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.o; g.K = (int)s.i;
     g.A = X; g.lda = s.i; g.major_a = MAJOR_K;
     g.B = W; g.ldb = s.i; g.major_b = MAJOR_K;
-    g.epi = epi; g.act = act; g.alpha = 1.f; g.bias = b;
+    g.epi = epi; g.act = act; g.alpha = 1.f; g.bias = b; g.tag = "gemm_fwd";
     g.out0 = A; g.ld_out0 = s.o; g.out1 = out1; g.ld_out1 = s.o; g.aux0 = aux; g.ld_aux0 = s.o; g.loss = loss;
     g.io_bf16 = g.dtype;
     return run_gemm(ctx, g);
@@ -707,7 +766,7 @@ int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, 
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.i; g.K = (int)s.o;
     g.A = dZ; g.lda = s.o; g.major_a = MAJOR_K;
     g.B = W; g.ldb = s.i; g.major_b = MAJOR_MN;
-    g.epi = epi; g.act = act; g.alpha = 1.f;
+    g.epi = epi; g.act = act; g.alpha = 1.f; g.tag = "gemm_dX";
     g.out0 = dX; g.ld_out0 = s.i; g.aux0 = Aprev; g.ld_aux0 = s.i;
     g.io_bf16 = g.dtype;
     return run_gemm(ctx, g);
@@ -718,9 +777,10 @@ int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, 
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.o; g.N = (int)s.i; g.K = (int)s.B;
     g.A = dZ; g.lda = s.o; g.major_a = MAJOR_MN;
     g.B = Xin; g.ldb = s.i; g.major_b = MAJOR_MN;
-    g.epi = EPI_ATOMIC; g.alpha = 1.f; g.out0 = dW; g.ld_out0 = s.i;
+    g.epi = EPI_ATOMIC; g.alpha = 1.f; g.out0 = dW; g.ld_out0 = s.i; g.tag = "gemm_dW";
     TRY(run_gemm(ctx, g));
     if (db) {
+        ProfScope prof_(ctx, "col_sums_db", 0.0, (s.dtype == TOPS_BF16 ? 2.0 : 4.0) * (double)s.B * s.o);
         float* ws = nullptr;
         CUDA_TRY(ctx, cudaMallocAsync((void**)&ws, sizeof(float) * 64 * (size_t)s.o, ctx->stream));
         if (s.dtype == TOPS_BF16) k::col_sums_bf16(lc_of(ctx), dZ, s.B, s.o, db, ws);

@@ -23,6 +23,7 @@ struct GemmCall {
     int split_k;    // 0 = choose automatically (only EPI_ATOMIC may split)
     int block_n;    // 0 = choose automatically, else 128 or 256
     int max_ctas;   // 0 = number of SMs
+    const char* tag;   // profiling label (tops_profile_*), may be NULL
 };
 
 // returns 0 on success; -1 if the problem cannot be expressed as TMA tensor maps (caller uses the SIMT kernel);

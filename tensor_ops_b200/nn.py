@@ -195,6 +195,28 @@ def fflayer_fwd_grad(X: CuTensor, W: CuTensor, b: CuTensor, dA: CuTensor, act: i
     return tuple(res)
 
 
+def fflayer_fwd_grad_host(ctx: Context, X_host, W: CuTensor, b: CuTensor, dA_host, act: int = L.ACT_LOGISTIC, grads_out=None,
+                          allreduce: Optional[Callable[[], None]] = None, workspace=None):
+    """Host-buffer entry point of the batched fwd+grad: `fromList` the batch (X, dA: C-contiguous fp32 host arrays, pinned
+    for async copies), run `tops_fflayer_fwd_grad` on the device, `toList` the packed parameter gradient [dW‖db] into
+    `grads_out`.  `workspace` = (X_dev, dA_dev, A_dev, dX_dev, packed_dev) re-uses device buffers between steps;
+    `allreduce` (data-parallel runs) is called on the packed gradient before it is read back."""
+    import numpy as np
+    B, i = X_host.shape
+    o = W.shape[0]
+    if workspace is None:
+        workspace = (ctx.empty((B, i)), ctx.empty((B, o)), ctx.empty((B, o)), ctx.empty((B, i)), ctx.empty((o * i + o,)))
+    Xd, dAd, Ad, dXd, packed = workspace
+    Xd.upload(X_host)
+    dAd.upload(dA_host)
+    fflayer_fwd_grad(Xd, W, b, dAd, act, out=(Ad, dXd, packed.view(0, (o, i)), packed.view(o * i, (o,))))
+    if allreduce is not None:
+        allreduce()
+    if grads_out is None:
+        grads_out = np.empty(o * i + o, dtype=np.float32)
+    return packed.download_into(grads_out)
+
+
 def fflayer_grad(X: CuTensor, W: CuTensor, b: CuTensor, dA: CuTensor, act: int = L.ACT_LOGISTIC, A_saved: Optional[CuTensor] = None):
     """gradTOp' of the layer (tops_fflayer_grad); recomputes the forward unless A_saved is given."""
     ctx = X.ctx

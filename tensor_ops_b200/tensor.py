@@ -41,6 +41,14 @@ class Context:
     def precision(self) -> int: return L.lib.tops_get_precision(self.h)
     def launch_count(self) -> int: return L.lib.tops_launch_count(self.h)
     def sm_count(self) -> int: return L.lib.tops_device_sm_count(self.h)
+    def profile(self, on: bool): self.check(L.lib.tops_profile_enable(self.h, int(on)))
+
+    def profile_summary(self) -> dict:
+        """Per-tag device times of the launches since profiling was enabled (synchronises)."""
+        import json
+        buf = C.create_string_buffer(8192)
+        self.check(L.lib.tops_profile_summary(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     # ---- construction
     def empty(self, dims: Sequence[int], dtype: int = L.F32) -> "CuTensor":
@@ -146,6 +154,20 @@ class CuTensor:
         out = np.empty(self.shape, dtype=np.float32)
         self.ctx.check(L.lib.tops_download(self.ctx.h, self.b, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
+
+    def upload(self, host: np.ndarray, sync: bool = False) -> "CuTensor":
+        """host -> this tensor's HBM (async on the context's stream when `host` is pinned)."""
+        assert host.flags["C_CONTIGUOUS"]
+        self.ctx.check(L.lib.tops_upload(self.ctx.h, self.b, host.ctypes.data_as(C.c_void_p), host.nbytes))
+        if sync:
+            self.ctx.sync()
+        return self
+
+    def download_into(self, host: np.ndarray) -> np.ndarray:
+        """HBM -> an existing (ideally pinned) host array; synchronises."""
+        assert host.flags["C_CONTIGUOUS"]
+        self.ctx.check(L.lib.tops_download(self.ctx.h, self.b, host.ctypes.data_as(C.c_void_p), host.nbytes))
+        return host
 
     def index(self, idx: Sequence[int]) -> float:
         """`(!)` (Types.hs:107-109)."""
