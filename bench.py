@@ -184,7 +184,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     ctx = tb.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # one explicit (non-default) torch stream carries everything: the library's kernels, the NCCL all-reduce and the
+    # timing events.  (The legacy default stream has handle 0, which tops_set_stream reads as "use the context's own".)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     prec = {"tf32x3": tb.PREC_TF32X3, "tf32": tb.PREC_TF32, "simt": tb.PREC_FP32_SIMT}[args.precision]
     ctx.set_precision(prec)
 

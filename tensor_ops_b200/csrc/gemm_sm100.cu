@@ -121,15 +121,12 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
             if (split < 1) split = 1;
         }
     }
-    if (c.epi == EPI_ATOMIC && c.passes == 3) {
-        // TMEM accumulation truncates (error grows linearly with the chain length, measured ~2e-8 per MMA):
-        // keep each fp32-grade chain <= 1024 K-elements and let the fp32 atomics (round-to-nearest) do the rest.
-        const int min_split = (p.num_k_blocks + 31) / 32;
-        if (split < min_split) split = min_split;
-    }
     if (split > p.num_k_blocks) split = p.num_k_blocks;
     p.kb_per_split = (p.num_k_blocks + split - 1) / split;
     p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+    // 3-pass: TMEM accumulation truncates (~2e-8 relative per MMA, linear in the chain length), so a chunk of
+    // chunk_kb k-blocks (12 MMAs each) is promoted to round-to-nearest fp32 register sums; 4 k-blocks = 128 K-elements.
+    p.chunk_kb = c.chunk_kb > 0 ? c.chunk_kb : 4;
     p.epi = c.epi; p.act = c.act; p.alpha = c.alpha; p.beta = c.beta;
     p.out0 = c.out0; p.ld_out0 = c.ld_out0;
     p.out1 = c.out1; p.ld_out1 = c.ld_out1;

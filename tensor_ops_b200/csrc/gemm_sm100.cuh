@@ -14,8 +14,16 @@
 //   warp 0      TMA producer      global -> 128B-swizzled smem ring (mbarrier full[])
 //   warp 1      MMA issuer        one thread issues tcgen05.mma into TMEM, commits to empty[] / tmem_full[]
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue          tcgen05.ld -> registers -> fused bias / logistic / VJP math -> global
-//   warps 8-11  (3-pass only) splitter: lo = x - trunc_tf32(x) into a second tile (ready[]); the raw tile serves as hi
+//   1-pass (TF32 / bf16 throughput modes), 256 threads:
+//     warps 4-7   epilogue        tcgen05.ld -> registers -> fused bias / logistic / VJP math -> global; the whole K range
+//                                 of a work item accumulates in one TMEM buffer, double-buffered across work items
+//   3-pass (3xTF32, the fp32-grade parity mode), 512 threads, registers rebalanced with setmaxnreg:
+//     warps 4-11  epilogue        The tensor core's accumulator add TRUNCATES (measured: error grows linearly, ~2e-8 relative
+//                                 per MMA; 8e-6 after K = 1024), so TMEM only ever holds a CHUNK of `chunk_kb` k-blocks.  Each
+//                                 chunk is drained with tcgen05.ld and added, round-to-nearest fp32, into register accumulators
+//                                 (128 per thread: warp w owns TMEM lane quarter w%4 and column half (w-4)/4) while the MMA
+//                                 warp fills the other TMEM buffer; the fused epilogue math runs from the registers.
+//     warps 12-15 splitter        lo = x - trunc_tf32(x) into a second tile (ready[]); the raw tile serves as hi
 #pragma once
 
 #include <cuda_bf16.h>
@@ -41,6 +49,7 @@ struct GemmParams {
     int num_k_blocks;   // ceil(K / KB_ELEMS)
     int split_k;        // number of K partitions (>= 1)
     int kb_per_split;   // k-blocks per partition
+    int chunk_kb;       // 3-pass only: k-blocks accumulated in TMEM before promotion to fp32 registers (>= 1)
     int epi, act;
     float alpha, beta;
     void* out0; long long ld_out0;
@@ -63,7 +72,8 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (PASSES == 3 ? 2 : 1);
-    static constexpr int NUM_THREADS = PASSES == 3 ? 384 : 256;
+    static constexpr int NUM_THREADS = PASSES == 3 ? 512 : 256;
+    static constexpr int EPI_THREADS = PASSES == 3 ? 256 : 128;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
@@ -145,13 +155,87 @@ __device__ __forceinline__ void st_row32(void* base, long long ld, int row, int 
     }
 }
 
+// Fused epilogue math for 32 consecutive columns [col, col+32) of one output row.  v = accumulator values (fp32).
+__device__ __forceinline__ void epi_apply32(const GemmParams& p, int row, int col, bool vec, float (&v)[32], float& loss_acc) {
+    const bool bf = p.io_bf16 != 0;
+    auto load_aux = [&](float (&x)[32]) {
+        if (bf) ld_row32<true>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+        else ld_row32<false>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+    };
+    auto store = [&](void* base, long long ld, const float (&x)[32]) {
+        if (bf) st_row32<true>(base, ld, row, col, p.N, vec, x);
+        else st_row32<false>(base, ld, row, col, p.N, vec, x);
+    };
+    switch (p.epi) {
+        case EPI_STORE: {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] *= p.alpha;
+            if (p.aux0 != nullptr) {
+                float x[32];
+                load_aux(x);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = fmaf(p.beta, x[e], v[e]);
+            }
+            store(p.out0, p.ld_out0, v);
+        } break;
+        case EPI_ATOMIC: {
+            float* o = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out0 + col;
+            if (vec && col + 32 <= p.N) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    ptx::red_add_v4(o + g * 4, p.alpha * v[g * 4], p.alpha * v[g * 4 + 1], p.alpha * v[g * 4 + 2], p.alpha * v[g * 4 + 3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) if (col + e < p.N) atomicAdd(o + e, p.alpha * v[e]);
+            }
+        } break;
+        case EPI_BIAS_ACT:
+        case EPI_BIAS_ACT_DZ:
+        case EPI_BIAS_ACT_SE: {
+            if (p.bias != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = act_apply(p.act, v[e]);
+            store(p.out0, p.ld_out0, v);
+            if (p.epi != EPI_BIAS_ACT) {
+                float x[32];
+                load_aux(x);
+                if (p.epi == EPI_BIAS_ACT_DZ) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = x[e] * act_deriv_from_out(p.act, v[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float d = (col + e < p.N) ? x[e] - v[e] : 0.f;   // squaredError: NeuralNet.hs:61-68
+                        loss_acc = fmaf(d, d, loss_acc);
+                        v[e] = -2.0f * d * act_deriv_from_out(p.act, v[e]);
+                    }
+                }
+                store(p.out1, p.ld_out1, v);
+            }
+        } break;
+        case EPI_MUL_DACT: {
+            float x[32];
+            load_aux(x);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] *= act_deriv_from_out(p.act, x[e]);
+            store(p.out0, p.ld_out0, v);
+        } break;
+        default: break;
+    }
+}
+
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES>::NUM_THREADS), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES>;
     constexpr bool kBF16 = sizeof(T) == 2;
+    constexpr bool kChunked = PASSES == 3;   // TMEM holds one chunk; the running sum lives in epilogue registers
     constexpr int BM = Cfg::BM;
     constexpr int KB = Cfg::KB_ELEMS;
+    constexpr int kSplitWarp0 = 12;          // first splitter warp (3-pass layout)
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -179,7 +263,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], 128);
+            ptx::mbar_init(&tmem_empty[a], Cfg::EPI_THREADS);
         }
         ptx::fence_barrier_init();
     }
@@ -194,10 +278,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int total_work = num_tiles * p.split_k;
+    const int chunk_kb = kChunked ? p.chunk_kb : (1 << 30);
 
-    if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
+    if (warp < 4) {
+        if constexpr (kChunked) ptx::setmaxnreg_dec<64>();
+        if (warp == 0 && lane == 0) {
+            // ===================================================== TMA producer
             int s = 0; uint32_t ph = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int tile = w % num_tiles, split = w / num_tiles;
@@ -226,10 +312,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
-        }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
+            // ===================================================== MMA issuer
             constexpr uint32_t idesc = ptx::make_idesc(kBF16 ? 1u : 2u, MA == MAJOR_MN, MB == MAJOR_MN, BM, BN);
             // byte advance of the descriptor start address per UMMA_K step, and the LBO/SBO of each layout
             constexpr uint32_t a_step = (MA == MAJOR_K) ? 32u : (uint32_t)Cfg::UMMA_K * 128u;
@@ -239,43 +323,46 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // MN-major 32-bit operands must use the 32B-atom flavour of the 128B swizzle (4-row atoms, SBO = 512)
             constexpr uint32_t a_lt = (MA == MAJOR_MN && !kBF16) ? 1u : 2u, b_lt = (MB == MAJOR_MN && !kBF16) ? 1u : 2u;
             constexpr uint32_t a_sbo = a_lt == 1u ? 512u : 1024u, b_sbo = b_lt == 1u ? 512u : 1024u;
-            int s = 0; uint32_t ph = 0; int it = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+            int s = 0; uint32_t ph = 0; int it = 0;   // `it` counts accumulation units: work items (1-pass) or chunks (3-pass)
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int split = w / num_tiles;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
-                const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, wd, 0x200 + acc);
-                ptx::tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                uint32_t first = 1;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(PASSES == 3 ? &ready_bar[s] : &full_bar[s], ph, wd, 0x300 + s);
+                for (int kc = kb0; kc < kb1; kc += chunk_kb, ++it) {
+                    const int kce = min(kc + chunk_kb, kb1);
+                    const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+                    ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, wd, 0x200 + acc);
                     ptx::tcgen05_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    uint32_t first = 1;
+                    for (int kb = kc; kb < kce; ++kb) {
+                        ptx::mbar_wait(PASSES == 3 ? &ready_bar[s] : &full_bar[s], ph, wd, 0x300 + s);
+                        ptx::tcgen05_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                        const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
-                    for (int pass = 0; pass < PASSES; ++pass) {
-                        // pass 0: A_hi*B_hi   pass 1: A_lo*B_hi   pass 2: A_hi*B_lo
-                        const uint32_t pa = sa + (pass == 1 ? Cfg::RAW_BYTES : 0);
-                        const uint32_t pb = sb + (pass == 2 ? Cfg::RAW_BYTES : 0);
+                        for (int pass = 0; pass < PASSES; ++pass) {
+                            // pass 0: A_hi*B_hi   pass 1: A_lo*B_hi   pass 2: A_hi*B_lo
+                            const uint32_t pa = sa + (pass == 1 ? Cfg::RAW_BYTES : 0);
+                            const uint32_t pb = sb + (pass == 2 ? Cfg::RAW_BYTES : 0);
 #pragma unroll
-                        for (int j = 0; j < Cfg::KSTEPS; ++j) {
-                            const uint64_t ad = ptx::make_smem_desc_sw128(pa + j * a_step, a_lbo, a_sbo, a_lt);
-                            const uint64_t bd = ptx::make_smem_desc_sw128(pb + j * b_step, b_lbo, b_sbo, b_lt);
-                            if constexpr (kBF16) ptx::umma_f16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-                            else ptx::umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-                            first = 0;
+                            for (int j = 0; j < Cfg::KSTEPS; ++j) {
+                                const uint64_t ad = ptx::make_smem_desc_sw128(pa + j * a_step, a_lbo, a_sbo, a_lt);
+                                const uint64_t bd = ptx::make_smem_desc_sw128(pb + j * b_step, b_lbo, b_sbo, b_lt);
+                                if constexpr (kBF16) ptx::umma_f16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                else ptx::umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
                         }
+                        ptx::umma_commit(&empty_bar[s]);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
-                    ptx::umma_commit(&empty_bar[s]);
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    ptx::umma_commit(&tmem_full[acc]);
                 }
-                ptx::umma_commit(&tmem_full[acc]);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================================================== epilogue
+    } else if (!kChunked) {
+        // ===================================================== epilogue, 1-pass: warps 4-7, one TMEM buffer per work item
         const int q = warp & 3;   // TMEM lane quarter this warp may read
         const bool vec = p.vec_ok != 0;
         int it = 0;
@@ -298,71 +385,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float v[32];
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-                    switch (p.epi) {
-                        case EPI_STORE: {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) v[e] *= p.alpha;
-                            if (p.aux0 != nullptr) {
-                                float x[32];
-                                ld_row32<kBF16>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
-#pragma unroll
-                                for (int e = 0; e < 32; ++e) v[e] = fmaf(p.beta, x[e], v[e]);
-                            }
-                            if (p.io_bf16) st_row32<true>(p.out0, p.ld_out0, row, col, p.N, vec, v);
-                            else st_row32<false>(p.out0, p.ld_out0, row, col, p.N, vec, v);
-                        } break;
-                        case EPI_ATOMIC: {
-                            float* o = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out0 + col;
-                            if (vec && col + 32 <= p.N) {
-#pragma unroll
-                                for (int g = 0; g < 8; ++g)
-                                    ptx::red_add_v4(o + g * 4, p.alpha * v[g * 4], p.alpha * v[g * 4 + 1], p.alpha * v[g * 4 + 2], p.alpha * v[g * 4 + 3]);
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 32; ++e) if (col + e < p.N) atomicAdd(o + e, p.alpha * v[e]);
-                            }
-                        } break;
-                        case EPI_BIAS_ACT:
-                        case EPI_BIAS_ACT_DZ:
-                        case EPI_BIAS_ACT_SE: {
-                            if (p.bias != nullptr) {
-#pragma unroll
-                                for (int e = 0; e < 32; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
-                            }
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) v[e] = act_apply(p.act, v[e]);
-                            if (p.io_bf16) st_row32<true>(p.out0, p.ld_out0, row, col, p.N, vec, v);
-                            else st_row32<false>(p.out0, p.ld_out0, row, col, p.N, vec, v);
-                            if (p.epi != EPI_BIAS_ACT) {
-                                float x[32];
-                                if (p.io_bf16) ld_row32<true>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
-                                else ld_row32<false>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
-                                if (p.epi == EPI_BIAS_ACT_DZ) {
-#pragma unroll
-                                    for (int e = 0; e < 32; ++e) v[e] = x[e] * act_deriv_from_out(p.act, v[e]);
-                                } else {
-#pragma unroll
-                                    for (int e = 0; e < 32; ++e) {
-                                        const float d = (col + e < p.N) ? x[e] - v[e] : 0.f;   // squaredError: NeuralNet.hs:61-68
-                                        loss_acc = fmaf(d, d, loss_acc);
-                                        v[e] = -2.0f * d * act_deriv_from_out(p.act, v[e]);
-                                    }
-                                }
-                                if (p.io_bf16) st_row32<true>(p.out1, p.ld_out1, row, col, p.N, vec, v);
-                                else st_row32<false>(p.out1, p.ld_out1, row, col, p.N, vec, v);
-                            }
-                        } break;
-                        case EPI_MUL_DACT: {
-                            float x[32];
-                            if (p.io_bf16) ld_row32<true>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
-                            else ld_row32<false>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) v[e] *= act_deriv_from_out(p.act, x[e]);
-                            if (p.io_bf16) st_row32<true>(p.out0, p.ld_out0, row, col, p.N, vec, v);
-                            else st_row32<false>(p.out0, p.ld_out0, row, col, p.N, vec, v);
-                        } break;
-                        default: break;
-                    }
+                    epi_apply32(p, row, col, vec, v, loss_acc);
                 }
             }
             ptx::tcgen05_fence_before();
@@ -373,9 +396,60 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
             if (lane == 0) atomicAdd(p.loss, loss_acc);
         }
-    } else if (PASSES == 3 && warp >= 8) {
-        // ===================================================== hi/lo splitter (3xTF32)
-        const int t = threadIdx.x - 256;   // 0..127
+    } else if (warp < kSplitWarp0) {
+        // ===================================================== epilogue, 3-pass: warps 4-11, chunked promotion to registers
+        ptx::setmaxnreg_inc<192>();
+        constexpr int HC = BN / 2;            // columns per warp: half of the tile
+        const int q = warp & 3;               // TMEM lane quarter (hardware rule: warp w reads lanes 32*(w%4)..+31)
+        const int half = (warp - 4) >> 2;     // column half
+        const bool vec = p.vec_ok != 0;
+        int it = 0;
+        float loss_acc = 0.f;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int tile = w % num_tiles, split = w / num_tiles;
+            const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+            float sum[HC];
+#pragma unroll
+            for (int e = 0; e < HC; ++e) sum[e] = 0.f;
+            for (int kc = kb0; kc < kb1; kc += chunk_kb, ++it) {
+                const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+                ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
+                ptx::tcgen05_fence_after();
+                const uint32_t t_row = tmem_base + acc * BN + half * HC + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+                for (int c = 0; c < HC / 16; ++c) {
+                    uint32_t raw[16];
+                    ptx::tmem_ld_32x32b_x16(t_row + c * 16, raw);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) sum[c * 16 + e] += __uint_as_float(raw[e]);   // fp32 add, round to nearest
+                }
+                ptx::tcgen05_fence_before();
+                ptx::mbar_arrive(&tmem_empty[acc]);
+            }
+            const int row = m0 + q * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < HC / 32; ++c) {
+                const int col = n0 + half * HC + c * 32;
+                if (row < p.M && col < p.N) {
+                    float v[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = sum[c * 32 + e];
+                    epi_apply32(p, row, col, vec, v, loss_acc);
+                }
+            }
+        }
+        if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+            if (lane == 0) atomicAdd(p.loss, loss_acc);
+        }
+    } else {
+        // ===================================================== hi/lo splitter (3xTF32): warps 12-15
+        ptx::setmaxnreg_dec<64>();
+        const int t = threadIdx.x - kSplitWarp0 * 32;   // 0..127
         int s = 0; uint32_t ph = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int split = w / num_tiles;

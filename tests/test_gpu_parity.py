@@ -338,7 +338,8 @@ def test_lift_catalogue_and_interpreter(ctx):
 def test_softmax_reference_form(ctx):
     rng = np.random.default_rng(14)
     z = rng.normal(size=(40, 10)); e = np.exp(z)
-    close(ctx.from_numpy(z)._new(tb._lib.lib.tops_map_rows_softmax, ctx.from_numpy(z).b), e / e.sum(1, keepdims=True), 1e-6, "softmax rows")
+    zt = ctx.from_numpy(z)   # keep the handle alive: `.b` of a temporary would be released before the call
+    close(zt._new(tb._lib.lib.tops_map_rows_softmax, zt.b), e / e.sum(1, keepdims=True), 1e-6, "softmax rows")
     # the reference softmax TOp on one sample, through the generic algebra
     v = rng.normal(size=10)
     close(TO.runTOp(nn.softmax(), [ctx.from_numpy(v)])[0], np.exp(v) / np.exp(v).sum(), 1e-6, "softmax TOp")
