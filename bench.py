@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["B"], help="rows per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the single-pass TF32 side measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -170,7 +171,7 @@ def main():
     import torch
     import torch.distributed as dist
     import tensor_ops_b200 as tb
-    from tensor_ops_b200 import nn
+    from tensor_ops_b200 import nn, dp
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus != world:
@@ -199,15 +200,15 @@ def main():
     W = ctx.rand_normal((o, i), 0.0, 0.5, seed=1)
     b = ctx.rand_normal((o,), 0.0, 0.5, seed=2)
     A = ctx.empty((B, o)); dX = ctx.empty((B, i))
-    packed_t = torch.zeros(o * i + o, dtype=torch.float32, device=dev)       # [dW‖db]: one buffer, one all-reduce
+    layout = dp.PackedLayout.for_layers([(o, i)])                            # [dW‖db]: one buffer, one all-reduce
+    packed_t = torch.zeros(layout.numel, dtype=torch.float32, device=dev)
     packed = ctx.wrap_torch(packed_t)
-    dWv, dbv = packed.view(0, (o, i)), packed.view(o * i, (o,))
+    dWv, dbv = layout.views(packed)
     outs = (A, dX, dWv, dbv)
 
     def step():
         nn.fflayer_fwd_grad(X, W, b, dA, out=outs)
-        if world > 1:
-            dist.all_reduce(packed_t)
+        dp.allreduce_sum_(packed_t)
 
     def barrier():
         torch.cuda.synchronize()
@@ -242,6 +243,32 @@ def main():
     ms_per_step = ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
 
+    # ---- side measurement: the same step in single-pass TF32 (throughput mode; NOT the headline — its parity error is ~7e-4)
+    side = None
+    if args.precision == "tf32x3" and not args.no_side:
+        ctx.set_precision(tb.PREC_TF32)
+        for _ in range(3):
+            step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.profile(True)
+        s0.record()
+        for _ in range(args.steps):
+            step()
+        s1.record()
+        barrier()
+        sms = s0.elapsed_time(s1) / args.steps
+        sprof = ctx.profile_summary()
+        ctx.profile(False)
+        ctx.set_precision(prec)
+        if world > 1:
+            t = torch.tensor([sms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sms = float(t.item())
+        side = {"precision": "single-pass TF32 on tcgen05 (operands truncated to TF32: ~7e-4 relative error, fails the 1e-5 parity bar)",
+                "ms_per_step": sms, "value": B * world / (sms * 1e-3), "unit": "samples/s",
+                "per_kernel_ms": {k: v["ms"] / v["launches"] for k, v in sprof.items()}}
+
     # ---- e2e: host buffers in, gradient out, copies inside the timed region (same step, same sizes)
     e2e = None
     if not args.no_e2e:
@@ -252,7 +279,7 @@ def main():
         e2e_steps = max(3, min(args.steps, 10))
 
         def e2e_step():
-            g = nn.fflayer_fwd_grad_host(ctx, Xn, W, b, dAn, grads_out=gn, allreduce=(lambda: dist.all_reduce(packed_t)) if world > 1 else None,
+            g = nn.fflayer_fwd_grad_host(ctx, Xn, W, b, dAn, grads_out=gn, allreduce=(lambda: dp.allreduce_sum_(packed_t)) if world > 1 else None,
                                          workspace=(X, dA, A, dX, packed))
             return g
         for _ in range(2):
@@ -304,6 +331,12 @@ def main():
                        "l2": "inputs larger than L2: X and dA are 256 MiB each per step vs 126 MB L2"},
             "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
             "algorithmic_flop_per_step": 6.0 * B * i * o, "tflops_step": 6.0 * B * i * o / (ms_per_step * 1e-3) / 1e12}
+    if side:
+        gs = {k: v for k, v in side["per_kernel_ms"].items() if k.startswith("gemm_")}
+        kdom = max(gs, key=gs.get)
+        side["roofline"] = {"kernel": kdom, "kernel_ms": gs[kdom], "achieved": 2.0 * B * i * o / (gs[kdom] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                            "frac": 2.0 * B * i * o / (gs[kdom] * 1e-3) / 1e12 / peak}
+        line["throughput_mode"] = side
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,65 @@
+"""Data-parallel plumbing for the batched ffLayer/MLP gradient: one process per GPU, the batch axis is
+sharded, parameters are replicated, and the parameter gradients of all layers travel in ONE packed fp32 buffer
+`[dW0‖db0‖dW1‖db1‖…]` that is all-reduced (sum) once per step.
+
+The reference has no parallelism of any kind (single process; `par`/`forkIO` appear nowhere) — the sum over samples
+that `trainNetwork`'s fold performs one sample at a time (app/Dots.hs:74-80) is what the all-reduce completes here.
+Only torch.distributed is used (NCCL on GPUs; gloo in the CPU tests); no device code lives in this module.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_range(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous row range [lo, hi) of a batch of `n_rows` samples owned by `rank`; the remainder goes to the
+    first ranks, so sizes differ by at most one and every row is owned exactly once."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(n_rows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class PackedLayout:
+    """Offsets of a list of parameter-shaped tensors inside one flat buffer."""
+
+    def __init__(self, shapes: Sequence[Sequence[int]]):
+        self.shapes = [tuple(int(d) for d in s) for s in shapes]
+        self.offsets: List[int] = []
+        off = 0
+        for s in self.shapes:
+            self.offsets.append(off)
+            off += int(np.prod(s)) if len(s) else 1
+        self.numel = off
+
+    @staticmethod
+    def for_layers(layer_dims: Sequence[Tuple[int, int]]) -> "PackedLayout":
+        """layer_dims = [(o, i), ...]  ->  [dW0[o,i], db0[o], dW1, db1, ...] (the order netGrad returns them,
+        FeedForward.hs:178-199)."""
+        shapes: List[Tuple[int, ...]] = []
+        for o, i in layer_dims:
+            shapes += [(o, i), (o,)]
+        return PackedLayout(shapes)
+
+    def views(self, packed):
+        """Split a CuTensor (via .view), a torch tensor or a NumPy array of `numel` elements into per-parameter views."""
+        out = []
+        for s, off in zip(self.shapes, self.offsets):
+            n = int(np.prod(s)) if len(s) else 1
+            if hasattr(packed, "view") and hasattr(packed, "ctx"):        # CuTensor
+                out.append(packed.view(off, s))
+            else:                                                          # torch / numpy: slicing keeps aliasing
+                out.append(packed[off:off + n].reshape(s))
+        return out
+
+
+def allreduce_sum_(packed_torch, group=None):
+    """In-place sum over ranks of the packed gradient buffer (torch tensor; NCCL on the current CUDA stream, or gloo on
+    CPU).  No-op without an initialised process group (single GPU)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed_torch, op=dist.ReduceOp.SUM, group=group)
+    return packed_torch
