@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -28,7 +29,8 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // 2-D row-major tensor [outer, inner] with leading dimension ld (elements); box = box_inner x box_outer, 128B swizzle.
-bool make_map(CUtensorMap* m, int dtype, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, bool atom32) {
+enum Swz { SWZ_128 = 0, SWZ_128_ATOM32 = 1, SWZ_64 = 2 };
+bool make_map(CUtensorMap* m, int dtype, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swz) {
     auto enc = get_encode();
     if (!enc) return false;
     const size_t es = dtype == 1 ? 2 : 4;
@@ -41,12 +43,13 @@ bool make_map(CUtensorMap* m, int dtype, const void* ptr, long long inner, long 
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                      const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swz == SWZ_128_ATOM32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swz == SWZ_64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
-cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES>;
     auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES>;
     static bool attr_set = false;   // per instantiation
@@ -55,28 +58,28 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
     return cudaGetLastError();
 }
 
 template <typename T, int MA, int MB>
-cudaError_t launch_major(int bn, int passes, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
+cudaError_t launch_major(int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         if (passes == 3) {
-            if (bn == 128) return launch_one<T, MA, MB, 128, 3, 3>(ta, tb, p, grid, st);
-            return launch_one<T, MA, MB, 256, 2, 3>(ta, tb, p, grid, st);
+            if (bn == 128) return launch_one<T, MA, MB, 128, 3, 3>(tm, p, grid, st);
+            return launch_one<T, MA, MB, 256, 2, 3>(tm, p, grid, st);
         }
     }
-    if (bn == 128) return launch_one<T, MA, MB, 128, 6, 1>(ta, tb, p, grid, st);
-    return launch_one<T, MA, MB, 256, 4, 1>(ta, tb, p, grid, st);
+    if (bn == 128) return launch_one<T, MA, MB, 128, 6, 1>(tm, p, grid, st);
+    return launch_one<T, MA, MB, 256, 4, 1>(tm, p, grid, st);
 }
 
 template <typename T>
-cudaError_t launch_dtype(int ma, int mb, int bn, int passes, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid, cudaStream_t st) {
-    if (ma == MAJOR_K && mb == MAJOR_K) return launch_major<T, MAJOR_K, MAJOR_K>(bn, passes, ta, tb, p, grid, st);
-    if (ma == MAJOR_K && mb == MAJOR_MN) return launch_major<T, MAJOR_K, MAJOR_MN>(bn, passes, ta, tb, p, grid, st);
-    if (ma == MAJOR_MN && mb == MAJOR_K) return launch_major<T, MAJOR_MN, MAJOR_K>(bn, passes, ta, tb, p, grid, st);
-    return launch_major<T, MAJOR_MN, MAJOR_MN>(bn, passes, ta, tb, p, grid, st);
+cudaError_t launch_dtype(int ma, int mb, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+    if (ma == MAJOR_K && mb == MAJOR_K) return launch_major<T, MAJOR_K, MAJOR_K>(bn, passes, tm, p, grid, st);
+    if (ma == MAJOR_K && mb == MAJOR_MN) return launch_major<T, MAJOR_K, MAJOR_MN>(bn, passes, tm, p, grid, st);
+    if (ma == MAJOR_MN && mb == MAJOR_K) return launch_major<T, MAJOR_MN, MAJOR_K>(bn, passes, tm, p, grid, st);
+    return launch_major<T, MAJOR_MN, MAJOR_MN>(bn, passes, tm, p, grid, st);
 }
 
 }  // namespace
@@ -94,14 +97,27 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     if (bn == 0) bn = (c.N <= 128) ? 128 : 256;
     if (bn != 128 && bn != 256) return fail(-1, "gemm: block_n must be 128 or 256");
 
-    CUtensorMap ta, tb;
+    CUtensorMap tm[5];   // A, B, out0, out1, aux0
+    CUtensorMap &ta = tm[0], &tb = tm[1];
+    memset(tm, 0, sizeof tm);
     bool ok;
-    if (c.major_a == MAJOR_K) ok = make_map(&ta, c.dtype, c.A, c.K, c.M, c.lda, kb_elems, 128, false);
-    else ok = make_map(&ta, c.dtype, c.A, c.M, c.K, c.lda, kb_elems, kb_elems, c.dtype == 0);
+    if (c.major_a == MAJOR_K) ok = make_map(&ta, c.dtype, c.A, c.K, c.M, c.lda, kb_elems, 128, SWZ_128);
+    else ok = make_map(&ta, c.dtype, c.A, c.M, c.K, c.lda, kb_elems, kb_elems, c.dtype == 0 ? SWZ_128_ATOM32 : SWZ_128);
     if (!ok) return fail(-1, "gemm: operand A not expressible as a TMA tensor map (alignment/stride)");
-    if (c.major_b == MAJOR_K) ok = make_map(&tb, c.dtype, c.B, c.K, c.N, c.ldb, kb_elems, bn, false);
-    else ok = make_map(&tb, c.dtype, c.B, c.N, c.K, c.ldb, kb_elems, kb_elems, c.dtype == 0);
+    if (c.major_b == MAJOR_K) ok = make_map(&tb, c.dtype, c.B, c.K, c.N, c.ldb, kb_elems, bn, SWZ_128);
+    else ok = make_map(&tb, c.dtype, c.B, c.N, c.K, c.ldb, kb_elems, kb_elems, c.dtype == 0 ? SWZ_128_ATOM32 : SWZ_128);
     if (!ok) return fail(-1, "gemm: operand B not expressible as a TMA tensor map (alignment/stride)");
+    // epilogue tensors as 32x32-element boxes (fp32: 128-byte rows, SWIZZLE_128B; bf16: 64-byte rows, SWIZZLE_64B);
+    // if any of them cannot be mapped the kernel uses its direct register<->global epilogue instead
+    bool tma_epi = c.epi != EPI_ATOMIC && !c.no_tma_epilogue;
+    if (tma_epi) {
+        const int odt = c.io_bf16 ? 1 : 0, oswz = c.io_bf16 ? SWZ_64 : SWZ_128;
+        const bool has_out1 = c.epi == EPI_BIAS_ACT_DZ || c.epi == EPI_BIAS_ACT_SE;
+        const bool has_aux = has_out1 || c.epi == EPI_MUL_DACT || (c.epi == EPI_STORE && c.aux0 != nullptr);
+        tma_epi = make_map(&tm[2], odt, c.out0, c.N, c.M, c.ld_out0, 32, 32, oswz);
+        if (tma_epi && has_out1) tma_epi = make_map(&tm[3], odt, c.out1, c.N, c.M, c.ld_out1, 32, 32, oswz);
+        if (tma_epi && has_aux) tma_epi = make_map(&tm[4], odt, c.aux0, c.N, c.M, c.ld_aux0, 32, 32, oswz);
+    }
 
     GemmParams p{};
     p.M = c.M; p.N = c.N; p.K = c.K;
@@ -134,6 +150,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     p.bias = c.bias; p.loss = c.loss;
     p.io_bf16 = c.io_bf16;
     p.watchdog = watchdog_dev;
+    p.tma_epi = tma_epi ? 1 : 0;
     auto vec_ok = [&](const void* ptr, long long ld) {
         if (!ptr) return true;
         const int oes = c.io_bf16 ? 2 : 4;
@@ -145,8 +162,8 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     const int total = tiles * p.split_k;
     const int grid = total < ctas ? total : ctas;
     cudaError_t e;
-    if (c.dtype == 1) e = launch_dtype<__nv_bfloat16>(c.major_a, c.major_b, bn, 1, ta, tb, p, grid, stream);
-    else e = launch_dtype<float>(c.major_a, c.major_b, bn, c.passes == 3 ? 3 : 1, ta, tb, p, grid, stream);
+    if (c.dtype == 1) e = launch_dtype<__nv_bfloat16>(c.major_a, c.major_b, bn, 1, tm, p, grid, stream);
+    else e = launch_dtype<float>(c.major_a, c.major_b, bn, c.passes == 3 ? 3 : 1, tm, p, grid, stream);
     if (e != cudaSuccess) {
         if (err && errlen) snprintf(err, errlen, "gemm launch: %s", cudaGetErrorString(e));
         return (int)e;

@@ -59,6 +59,7 @@ struct GemmParams {
     float* loss;              // scalar accumulator (EPI_BIAS_ACT_SE)
     int io_bf16;              // out0/out1/aux0 are bf16 (bf16 pipelines); 0 = fp32
     int vec_ok;               // 16-byte vector access legal for out0/out1/aux0
+    int tma_epi;              // epilogue I/O goes through smem staging + TMA (tensor maps tmO0/tmO1/tmAux are valid)
     unsigned int* watchdog;   // mapped host memory, 2 words
 };
 
@@ -75,8 +76,14 @@ struct GemmCfg {
     static constexpr int NUM_THREADS = PASSES == 3 ? 512 : 256;
     static constexpr int EPI_THREADS = PASSES == 3 ? 256 : 128;
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+    static constexpr int BAR_BYTES = 512;
+    // epilogue staging: 32x32-element blocks (4 KiB fp32 / 2 KiB bf16) per epilogue warp, moved by TMA.
+    // 1-pass: one block for the aux operand (prefetched one chunk ahead) + one for outputs; 3-pass: one shared block.
+    static constexpr int EPI_WARPS = EPI_THREADS / 32;
+    static constexpr int EPI_NBUF = PASSES == 3 ? 1 : 2;
+    static constexpr int EPI_BYTES = EPI_WARPS * EPI_NBUF * 4096;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + EPI_BYTES + 1024 /*alignment slack*/;
+    static_assert(BAR_BYTES <= 1024 && (3 * STAGES + 4 + EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier area");
     static_assert(PASSES == 1 || (PASSES == 3 && sizeof(T) == 4), "3-pass split is an fp32 technique");
     static_assert(BN == 128 || BN == 256, "BN");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -155,38 +162,22 @@ __device__ __forceinline__ void st_row32(void* base, long long ld, int row, int 
     }
 }
 
-// Fused epilogue math for 32 consecutive columns [col, col+32) of one output row.  v = accumulator values (fp32).
-__device__ __forceinline__ void epi_apply32(const GemmParams& p, int row, int col, bool vec, float (&v)[32], float& loss_acc) {
-    const bool bf = p.io_bf16 != 0;
-    auto load_aux = [&](float (&x)[32]) {
-        if (bf) ld_row32<true>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
-        else ld_row32<false>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
-    };
-    auto store = [&](void* base, long long ld, const float (&x)[32]) {
-        if (bf) st_row32<true>(base, ld, row, col, p.N, vec, x);
-        else st_row32<false>(base, ld, row, col, p.N, vec, x);
-    };
+// ---------------------------------------------------------------------------------------------- fused epilogue
+__device__ __forceinline__ bool epi_has_aux(const GemmParams& p) {
+    return p.epi == EPI_BIAS_ACT_DZ || p.epi == EPI_BIAS_ACT_SE || p.epi == EPI_MUL_DACT || (p.epi == EPI_STORE && p.aux0 != nullptr);
+}
+__device__ __forceinline__ bool epi_has_out1(const GemmParams& p) { return p.epi == EPI_BIAS_ACT_DZ || p.epi == EPI_BIAS_ACT_SE; }
+
+// Math for 32 consecutive columns [col, col+32) of one output row (every epilogue except EPI_ATOMIC).
+//   in : v = accumulators, x = aux values (if epi_has_aux)        out: v = out0 values, x = out1 values (if epi_has_out1)
+__device__ __forceinline__ void epi_math32(const GemmParams& p, bool row_ok, int col, float (&v)[32], float (&x)[32], float& loss_acc) {
     switch (p.epi) {
         case EPI_STORE: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] *= p.alpha;
             if (p.aux0 != nullptr) {
-                float x[32];
-                load_aux(x);
 #pragma unroll
                 for (int e = 0; e < 32; ++e) v[e] = fmaf(p.beta, x[e], v[e]);
-            }
-            store(p.out0, p.ld_out0, v);
-        } break;
-        case EPI_ATOMIC: {
-            float* o = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out0 + col;
-            if (vec && col + 32 <= p.N) {
-#pragma unroll
-                for (int g = 0; g < 8; ++g)
-                    ptx::red_add_v4(o + g * 4, p.alpha * v[g * 4], p.alpha * v[g * 4 + 1], p.alpha * v[g * 4 + 2], p.alpha * v[g * 4 + 3]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) if (col + e < p.N) atomicAdd(o + e, p.alpha * v[e]);
             }
         } break;
         case EPI_BIAS_ACT:
@@ -198,38 +189,159 @@ __device__ __forceinline__ void epi_apply32(const GemmParams& p, int row, int co
             }
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = act_apply(p.act, v[e]);
-            store(p.out0, p.ld_out0, v);
-            if (p.epi != EPI_BIAS_ACT) {
-                float x[32];
-                load_aux(x);
-                if (p.epi == EPI_BIAS_ACT_DZ) {
+            if (p.epi == EPI_BIAS_ACT_DZ) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = x[e] * act_deriv_from_out(p.act, v[e]);
-                } else {
+                for (int e = 0; e < 32; ++e) x[e] = x[e] * act_deriv_from_out(p.act, v[e]);
+            } else if (p.epi == EPI_BIAS_ACT_SE) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float d = (col + e < p.N) ? x[e] - v[e] : 0.f;   // squaredError: NeuralNet.hs:61-68
-                        loss_acc = fmaf(d, d, loss_acc);
-                        v[e] = -2.0f * d * act_deriv_from_out(p.act, v[e]);
-                    }
+                for (int e = 0; e < 32; ++e) {
+                    const float d = (row_ok && col + e < p.N) ? x[e] - v[e] : 0.f;   // squaredError: NeuralNet.hs:61-68
+                    loss_acc = fmaf(d, d, loss_acc);
+                    x[e] = -2.0f * d * act_deriv_from_out(p.act, v[e]);
                 }
-                store(p.out1, p.ld_out1, v);
             }
         } break;
         case EPI_MUL_DACT: {
-            float x[32];
-            load_aux(x);
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] *= act_deriv_from_out(p.act, x[e]);
-            store(p.out0, p.ld_out0, v);
         } break;
         default: break;
     }
 }
 
+// Direct (register <-> global) epilogue: used for EPI_ATOMIC and whenever the outputs cannot be described by TMA
+// tensor maps (unaligned base / leading dimension).  Row-per-thread accesses: correct everywhere, slow.
+__device__ __forceinline__ void epi_direct32(const GemmParams& p, int row, int col, bool vec, float (&v)[32], float& loss_acc) {
+    const bool bf = p.io_bf16 != 0;
+    if (p.epi == EPI_ATOMIC) {
+        float* o = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out0 + col;
+        if (vec && col + 32 <= p.N) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                ptx::red_add_v4(o + g * 4, p.alpha * v[g * 4], p.alpha * v[g * 4 + 1], p.alpha * v[g * 4 + 2], p.alpha * v[g * 4 + 3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) if (col + e < p.N) atomicAdd(o + e, p.alpha * v[e]);
+        }
+        return;
+    }
+    float x[32];
+    if (epi_has_aux(p)) {
+        if (bf) ld_row32<true>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+        else ld_row32<false>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+    }
+    epi_math32(p, true, col, v, x, loss_acc);
+    if (bf) st_row32<true>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+    else st_row32<false>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+    if (epi_has_out1(p)) {
+        if (bf) st_row32<true>(p.out1, p.ld_out1, row, col, p.N, vec, x);
+        else st_row32<false>(p.out1, p.ld_out1, row, col, p.N, vec, x);
+    }
+}
+
+// Staging blocks are 32 rows x 32 elements, laid out the way the TMA swizzle modes expect so that both the thread side
+// (lane = row, 16-byte accesses) and the TMA side are bank-conflict free:
+//   fp32: 128-byte rows, SWIZZLE_128B: 16B chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
+//   bf16:  64-byte rows, SWIZZLE_64B : 16B chunk j of row r lives at r*64  + ((j ^ ((r >> 1) & 3)) << 4)
+__device__ __forceinline__ void stage_read_row(const uint8_t* buf, bool bf, int r, float (&x)[32]) {
+    if (bf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(buf + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                x[j * 8 + e * 2] = f.x; x[j * 8 + e * 2 + 1] = f.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 f = *reinterpret_cast<const float4*>(buf + r * 128 + ((j ^ (r & 7)) << 4));
+            x[j * 4] = f.x; x[j * 4 + 1] = f.y; x[j * 4 + 2] = f.z; x[j * 4 + 3] = f.w;
+        }
+    }
+}
+__device__ __forceinline__ void stage_write_row(uint8_t* buf, bool bf, int r, const float (&x)[32]) {
+    if (bf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(x[j * 8 + e * 2], x[j * 8 + e * 2 + 1]);
+            *reinterpret_cast<uint4*>(buf + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = u;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(buf + r * 128 + ((j ^ (r & 7)) << 4)) = make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
+    }
+}
+
+// Per-warp state of the TMA epilogue.
+struct EpiWarp {
+    uint8_t* aux_buf;      // staging block for the aux operand
+    uint8_t* out_buf;      // staging block for out0 / out1 (== aux_buf when the kernel has one block per warp)
+    uint64_t* aux_bar;     // mbarrier the aux TMA load completes on
+    uint32_t aux_count;    // aux loads consumed so far (parity of the next wait)
+    bool prefetched;       // the aux block of the chunk about to be processed is already in flight
+};
+
+__device__ __forceinline__ void epi_issue_aux(const GemmParams& p, const CUtensorMap* tmAux, EpiWarp& w, int row0, int col) {
+    ptx::mbar_arrive_expect_tx(w.aux_bar, p.io_bf16 ? 2048u : 4096u);
+    ptx::tma_load_2d(w.aux_buf, tmAux, w.aux_bar, col, row0);
+}
+
+// One 32x32 block of the output tile, warp-collective: rows row0..row0+31 (lane = row), columns col..col+31.
+//   v: this lane's accumulators.  next_col >= 0: column of the next block this warp will process in the same rows (its aux
+//   block is prefetched when the kernel has a separate aux staging block).
+__device__ __forceinline__ void epi_tma_block(const GemmParams& p, const CUtensorMap* tmO0, const CUtensorMap* tmO1, const CUtensorMap* tmAux,
+                                              EpiWarp& w, int lane, int row0, int col, int next_col, float (&v)[32], float& loss_acc,
+                                              volatile unsigned int* wd) {
+    const bool bf = p.io_bf16 != 0;
+    const bool has_aux = epi_has_aux(p), has_out1 = epi_has_out1(p);
+    const bool shared_buf = (w.aux_buf == w.out_buf);
+    float x[32];
+    if (has_aux) {
+        if (!w.prefetched) {
+            if (lane == 0) {
+                if (shared_buf) ptx::tma_store_wait_read();   // a store may still be reading the shared block
+                epi_issue_aux(p, tmAux, w, row0, col);
+            }
+        }
+        ptx::mbar_wait(w.aux_bar, w.aux_count & 1, wd, 0x600);
+        ++w.aux_count;
+        stage_read_row(w.aux_buf, bf, lane, x);
+        __syncwarp();
+        w.prefetched = false;
+        if (!shared_buf && next_col >= 0) {
+            if (lane == 0) epi_issue_aux(p, tmAux, w, row0, next_col);
+            w.prefetched = true;
+        }
+    }
+    epi_math32(p, row0 + lane < p.M, col, v, x, loss_acc);
+    if (lane == 0) ptx::tma_store_wait_read();
+    __syncwarp();
+    stage_write_row(w.out_buf, bf, lane, v);
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { ptx::tma_store_2d(tmO0, w.out_buf, col, row0); ptx::tma_store_commit(); }
+    if (has_out1) {
+        if (lane == 0) ptx::tma_store_wait_read();
+        __syncwarp();
+        stage_write_row(w.out_buf, bf, lane, x);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { ptx::tma_store_2d(tmO1, w.out_buf, col, row0); ptx::tma_store_commit(); }
+    }
+}
+
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES>::NUM_THREADS), 1)
-gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
+                 const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES>;
     constexpr bool kBF16 = sizeof(T) == 2;
     constexpr bool kChunked = PASSES == 3;   // TMEM holds one chunk; the running sum lives in epilogue registers
@@ -245,7 +357,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* ready_bar = bars + 2 * STAGES;         // [STAGES]  hi/lo split done (3-pass)
     uint64_t* tmem_full = bars + 3 * STAGES;         // [2]
     uint64_t* tmem_empty = bars + 3 * STAGES + 2;    // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    uint64_t* epi_bar = bars + 3 * STAGES + 4;       // [EPI_WARPS] aux-operand TMA loads of the epilogue warps
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4 + Cfg::EPI_WARPS);
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 1024;   // barriers occupy the first BAR_BYTES of a 1 KiB slot so the staging blocks stay 1024-aligned
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -254,6 +368,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
+        if (p.tma_epi) {
+            ptx::prefetch_tensormap(&tmO0);
+            if (epi_has_out1(p)) ptx::prefetch_tensormap(&tmO1);
+            if (epi_has_aux(p)) ptx::prefetch_tensormap(&tmAux);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -265,6 +384,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::mbar_init(&tmem_full[a], 1);
             ptx::mbar_init(&tmem_empty[a], Cfg::EPI_THREADS);
         }
+        for (int e = 0; e < Cfg::EPI_WARPS; ++e) ptx::mbar_init(&epi_bar[e], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -281,7 +401,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int chunk_kb = kChunked ? p.chunk_kb : (1 << 30);
 
     if (warp < 4) {
-        if constexpr (kChunked) ptx::setmaxnreg_dec<64>();
+        if constexpr (kChunked) ptx::setmaxnreg_dec<48>();
         if (warp == 0 && lane == 0) {
             // ===================================================== TMA producer
             int s = 0; uint32_t ph = 0;
@@ -365,32 +485,44 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================================================== epilogue, 1-pass: warps 4-7, one TMEM buffer per work item
         const int q = warp & 3;   // TMEM lane quarter this warp may read
         const bool vec = p.vec_ok != 0;
+        const bool tma = p.tma_epi != 0;
+        EpiWarp ew;
+        ew.aux_buf = epi_smem + (warp - 4) * (Cfg::EPI_NBUF * 4096);
+        ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * 4096;
+        ew.aux_bar = &epi_bar[warp - 4]; ew.aux_count = 0; ew.prefetched = false;
         int it = 0;
         float loss_acc = 0.f;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
             const int tile = w % num_tiles;
             const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
             const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+            const int row0 = m0 + q * 32;
+            const int row = row0 + lane;
+            const int ncols = min(BN, p.N - n0);                  // valid columns of this tile (warp-uniform)
+            const int nblk = row0 < p.M ? (ncols + 31) / 32 : 0;  // 32-column blocks this warp owns in this tile
+            if (tma && nblk > 0 && epi_has_aux(p)) {              // the first aux block does not depend on the accumulators
+                if (lane == 0) epi_issue_aux(p, &tmAux, ew, row0, n0);
+                ew.prefetched = true;
+            }
             ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
             ptx::tcgen05_fence_after();
-            const int row = m0 + q * 32 + lane;
             const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < nblk; ++c) {
                 uint32_t raw[32];
                 ptx::tmem_ld_32x32b_x32(t_row + c * 32, raw);
                 ptx::tmem_ld_wait();
                 const int col = n0 + c * 32;
-                if (row < p.M && col < p.N) {
-                    float v[32];
+                float v[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-                    epi_apply32(p, row, col, vec, v, loss_acc);
-                }
+                for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
+                if (tma) epi_tma_block(p, &tmO0, &tmO1, &tmAux, ew, lane, row0, col, c + 1 < nblk ? col + 32 : -1, v, loss_acc, wd);
+                else if (row < p.M) epi_direct32(p, row, col, vec, v, loss_acc);
             }
             ptx::tcgen05_fence_before();
             ptx::mbar_arrive(&tmem_empty[acc]);
         }
+        if (tma && lane == 0) ptx::tma_store_wait_all();
         if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
@@ -398,11 +530,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp < kSplitWarp0) {
         // ===================================================== epilogue, 3-pass: warps 4-11, chunked promotion to registers
-        ptx::setmaxnreg_inc<192>();
+        ptx::setmaxnreg_inc<208>();
         constexpr int HC = BN / 2;            // columns per warp: half of the tile
         const int q = warp & 3;               // TMEM lane quarter (hardware rule: warp w reads lanes 32*(w%4)..+31)
         const int half = (warp - 4) >> 2;     // column half
         const bool vec = p.vec_ok != 0;
+        const bool tma = p.tma_epi != 0;
+        EpiWarp ew;
+        ew.aux_buf = epi_smem + (warp - 4) * (Cfg::EPI_NBUF * 4096);
+        ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * 4096;
+        ew.aux_bar = &epi_bar[warp - 4]; ew.aux_count = 0; ew.prefetched = false;
         int it = 0;
         float loss_acc = 0.f;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -429,18 +566,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ptx::tcgen05_fence_before();
                 ptx::mbar_arrive(&tmem_empty[acc]);
             }
-            const int row = m0 + q * 32 + lane;
+            const int row0 = m0 + q * 32;
+            const int row = row0 + lane;
+            if (row0 < p.M) {
 #pragma unroll
-            for (int c = 0; c < HC / 32; ++c) {
-                const int col = n0 + half * HC + c * 32;
-                if (row < p.M && col < p.N) {
-                    float v[32];
+                for (int c = 0; c < HC / 32; ++c) {
+                    const int col = n0 + half * HC + c * 32;
+                    if (col < p.N) {
+                        float v[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = sum[c * 32 + e];
-                    epi_apply32(p, row, col, vec, v, loss_acc);
+                        for (int e = 0; e < 32; ++e) v[e] = sum[c * 32 + e];
+                        if (tma) epi_tma_block(p, &tmO0, &tmO1, &tmAux, ew, lane, row0, col, -1, v, loss_acc, wd);
+                        else if (row < p.M) epi_direct32(p, row, col, vec, v, loss_acc);
+                    }
                 }
             }
         }
+        if (tma && lane == 0) ptx::tma_store_wait_all();
         if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
@@ -448,7 +590,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         // ===================================================== hi/lo splitter (3xTF32): warps 12-15
-        ptx::setmaxnreg_dec<64>();
+        ptx::setmaxnreg_dec<48>();
         const int t = threadIdx.x - kSplitWarp0 * 32;   // 0..127
         int s = 0; uint32_t ph = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
