@@ -180,6 +180,7 @@ int need_f32(tops_ctx* ctx, const tops_buf* x, const char* what) {
 
 // ---------------------------------------------------------------------------------------------- GEMM dispatch
 int run_gemm(tops_ctx* ctx, GemmCall c) {
+    if (c.colsum_fused) *c.colsum_fused = 0;
     if (c.M <= 0 || c.N <= 0) return TOPS_OK;
     const double es_in = c.dtype == 1 ? 2.0 : 4.0, es_out = c.io_bf16 ? 2.0 : 4.0;
     ProfScope prof_(ctx, c.tag ? c.tag : "gemm", 2.0 * c.M * c.N * (double)(c.K > 0 ? c.K : 0),
@@ -749,8 +750,10 @@ int layer_shapes(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops
 }
 
 // A = act(X W^T + b)  [optionally also dZ = dA ⊙ act'(A)]  — one GEMM, everything else in its epilogue
+// `db` (optional, epilogues with a dZ output only): column sums of dZ fused into the epilogue; *db_fused reports whether the
+// kernel produced them (the TMA epilogue does; the direct / SIMT paths leave it to col_sums).
 int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, const float* b, int act, int epi,
-             void* A, const void* aux, void* out1, float* loss) {
+             void* A, const void* aux, void* out1, float* loss, float* db = nullptr, int* db_fused = nullptr) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.o; g.K = (int)s.i;
     g.A = X; g.lda = s.i; g.major_a = MAJOR_K;
@@ -758,10 +761,16 @@ int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, 
     g.epi = epi; g.act = act; g.alpha = 1.f; g.bias = b; g.tag = "gemm_fwd";
     g.out0 = A; g.ld_out0 = s.o; g.out1 = out1; g.ld_out1 = s.o; g.aux0 = aux; g.ld_aux0 = s.o; g.loss = loss;
     g.io_bf16 = g.dtype;
+    if (db && out1 && s.B > 0) {
+        CUDA_TRY(ctx, cudaMemsetAsync(db, 0, sizeof(float) * (size_t)s.o, ctx->stream));
+        g.colsum = db; g.colsum_src = 2; g.colsum_fused = db_fused;
+    }
     return run_gemm(ctx, g);
 }
 // dX = dZ W  (optionally ⊙ act'(A_prev))
-int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, void* dX, int epi, int act, const void* Aprev) {
+// `db_prev` (optional, EPI_MUL_DACT only): the output IS dZ of the previous layer, so its column sums are that layer's db.
+int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, void* dX, int epi, int act, const void* Aprev,
+            float* db_prev = nullptr, int* db_fused = nullptr) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.i; g.K = (int)s.o;
     g.A = dZ; g.lda = s.o; g.major_a = MAJOR_K;
@@ -769,17 +778,21 @@ int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, 
     g.epi = epi; g.act = act; g.alpha = 1.f; g.tag = "gemm_dX";
     g.out0 = dX; g.ld_out0 = s.i; g.aux0 = Aprev; g.ld_aux0 = s.i;
     g.io_bf16 = g.dtype;
+    if (db_prev && epi == EPI_MUL_DACT && s.B > 0) {
+        CUDA_TRY(ctx, cudaMemsetAsync(db_prev, 0, sizeof(float) * (size_t)s.i, ctx->stream));
+        g.colsum = db_prev; g.colsum_src = 1; g.colsum_fused = db_fused;
+    }
     return run_gemm(ctx, g);
 }
 // dW = dZ^T Xin   (split-K over the batch, fp32 atomics into a zeroed output), db = column sums of dZ
-int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, float* dW, float* db) {
+int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, float* dW, float* db, bool db_done = false) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.o; g.N = (int)s.i; g.K = (int)s.B;
     g.A = dZ; g.lda = s.o; g.major_a = MAJOR_MN;
     g.B = Xin; g.ldb = s.i; g.major_b = MAJOR_MN;
     g.epi = EPI_ATOMIC; g.alpha = 1.f; g.out0 = dW; g.ld_out0 = s.i; g.tag = "gemm_dW";
     TRY(run_gemm(ctx, g));
-    if (db) {
+    if (db && !db_done) {
         ProfScope prof_(ctx, "col_sums_db", 0.0, (s.dtype == TOPS_BF16 ? 2.0 : 4.0) * (double)s.B * s.o);
         float* ws = nullptr;
         CUDA_TRY(ctx, cudaMallocAsync((void**)&ws, sizeof(float) * 64 * (size_t)s.o, ctx->stream));
@@ -818,8 +831,10 @@ extern "C" int tops_fflayer_fwd_grad(tops_ctx* ctx, const tops_buf* X, const top
     if (db) TRY(prep_out(ctx, db, TOPS_F32, 1, dbs));
     Tmp tmp; tops_buf* dZ = nullptr;
     TRY(alloc_buf(ctx, s.dtype, 2, dAo, &dZ)); tmp.keep(dZ);
-    TRY(fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, (*A)->data, dA->data, dZ->data, nullptr));
-    TRY(dw_db(ctx, s, dZ->data, X->data, (float*)(*dW)->data, db ? (float*)(*db)->data : nullptr));
+    int db_fused = 0;
+    TRY(fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, (*A)->data, dA->data, dZ->data, nullptr,
+                 db ? (float*)(*db)->data : nullptr, &db_fused));
+    TRY(dw_db(ctx, s, dZ->data, X->data, (float*)(*dW)->data, db ? (float*)(*db)->data : nullptr, db_fused != 0));
     if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
     return TOPS_OK;
 }
@@ -914,6 +929,13 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
     TRY(prep_out(ctx, loss_sum, TOPS_F32, 0, nullptr));
     float* lossp = (float*)(*loss_sum)->data;
     CUDA_TRY(ctx, cudaMemsetAsync(lossp, 0, 4, ctx->stream));
+    // gradient outputs first: the GEMM epilogues that produce a dZ also produce that layer's db (fused column sums)
+    std::vector<int> db_done(n, 0);
+    for (int l = 0; l < n; ++l) {
+        int64_t dWs[2] = {W[l]->dims[0], W[l]->dims[1]}, dbs[1] = {W[l]->dims[0]};
+        TRY(prep_out(ctx, &dW[l], TOPS_F32, 2, dWs));
+        TRY(prep_out(ctx, &db[l], TOPS_F32, 1, dbs));
+    }
     // ---- forward; the last layer's epilogue also produces the loss and dZ when the pairing allows
     const tops_buf* cur = X;
     tops_buf* dZ = nullptr;
@@ -927,7 +949,8 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
         if (last) { TRY(alloc_buf(ctx, TOPS_F32, 2, d, &dZ)); tmp.keep(dZ); }
         if (last && acts[l] != TOPS_ACT_SOFTMAX && loss == TOPS_LOSS_SQUARED_ERROR) {
             LayerShapes s{B, cur->dims[1], d[1], TOPS_F32};
-            TRY(fwd_gemm(ctx, s, cur->data, W[l]->data, (const float*)b[l]->data, acts[l], EPI_BIAS_ACT_SE, A->data, Y->data, dZ->data, lossp));
+            TRY(fwd_gemm(ctx, s, cur->data, W[l]->data, (const float*)b[l]->data, acts[l], EPI_BIAS_ACT_SE, A->data, Y->data, dZ->data, lossp,
+                         (float*)db[l]->data, &db_done[l]));
         } else if (last && acts[l] == TOPS_ACT_SOFTMAX && loss == TOPS_LOSS_CROSS_ENTROPY) {
             TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], nullptr));
             k::softmax_ce_rows(lc_of(ctx), (const float*)Zs[l]->data, (const float*)Y->data, (float*)A->data, (float*)dZ->data, lossp, B, d[1]);
@@ -948,10 +971,7 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
     // ---- reverse sweep: dW_l = dZ_l^T in_l, db_l = Σ dZ_l, dZ_{l-1} = (dZ_l W_l) ⊙ act'(A_{l-1}) fused in the GEMM epilogue
     for (int l = n - 1; l >= 0; --l) {
         LayerShapes s{B, W[l]->dims[1], W[l]->dims[0], TOPS_F32};
-        int64_t dWs[2] = {s.o, s.i}, dbs[1] = {s.o};
-        TRY(prep_out(ctx, &dW[l], TOPS_F32, 2, dWs));
-        TRY(prep_out(ctx, &db[l], TOPS_F32, 1, dbs));
-        TRY(dw_db(ctx, s, dZ->data, acts_in[l]->data, (float*)dW[l]->data, (float*)db[l]->data));
+        TRY(dw_db(ctx, s, dZ->data, acts_in[l]->data, (float*)dW[l]->data, (float*)db[l]->data, db_done[l] != 0));
         if (l > 0) {
             int64_t d[2] = {B, s.i};
             tops_buf* dZp = nullptr;
@@ -963,7 +983,8 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
                 k::softmax_vjp_rows(lc_of(ctx), (const float*)Zs[l - 1]->data, (const float*)dAp->data, (float*)dZp->data, B, s.i);
                 TRY(check_launch(ctx, "softmax_vjp"));
             } else {
-                TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, dZp->data, EPI_MUL_DACT, acts[l - 1], acts_in[l]->data));
+                TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, dZp->data, EPI_MUL_DACT, acts[l - 1], acts_in[l]->data,
+                            (float*)db[l - 1]->data, &db_done[l - 1]));
             }
             dZ = dZp;
         } else if (dX) {

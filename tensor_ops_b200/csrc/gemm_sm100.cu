@@ -58,7 +58,7 @@ cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cud
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+    kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], p);
     return cudaGetLastError();
 }
 
@@ -97,7 +97,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     if (bn == 0) bn = (c.N <= 128) ? 128 : 256;
     if (bn != 128 && bn != 256) return fail(-1, "gemm: block_n must be 128 or 256");
 
-    CUtensorMap tm[5];   // A, B, out0, out1, aux0
+    CUtensorMap tm[3];   // A, B, aux0
     CUtensorMap &ta = tm[0], &tb = tm[1];
     memset(tm, 0, sizeof tm);
     bool ok;
@@ -107,18 +107,18 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     if (c.major_b == MAJOR_K) ok = make_map(&tb, c.dtype, c.B, c.K, c.N, c.ldb, kb_elems, bn, SWZ_128);
     else ok = make_map(&tb, c.dtype, c.B, c.N, c.K, c.ldb, kb_elems, kb_elems, c.dtype == 0 ? SWZ_128_ATOM32 : SWZ_128);
     if (!ok) return fail(-1, "gemm: operand B not expressible as a TMA tensor map (alignment/stride)");
-    // epilogue tensors as 32x32-element boxes (fp32: 128-byte rows, SWIZZLE_128B; bf16: 64-byte rows, SWIZZLE_64B);
-    // if any of them cannot be mapped the kernel uses its direct register<->global epilogue instead
-    bool tma_epi = c.epi != EPI_ATOMIC && !c.no_tma_epilogue;
+    // Staged epilogue: outputs are transposed through shared memory and written with coalesced 16-byte stores, the aux operand
+    // (if any) is fetched by TMA as 32 x 32 boxes (fp32: 128-byte rows, SWIZZLE_128B; bf16: 64-byte rows, SWIZZLE_64B).
+    // Needs 16-byte aligned rows everywhere; otherwise the kernel falls back to its direct register<->global epilogue.
+    bool tma_epi = c.epi != EPI_ATOMIC && !c.no_tma_epilogue && (c.io_bf16 != 0) == (c.dtype == 1);   // staged blocks have the operand dtype
     if (tma_epi) {
-        const int odt = c.io_bf16 ? 1 : 0, oswz = c.io_bf16 ? SWZ_64 : SWZ_128;
+        const int oes = c.io_bf16 ? 2 : 4;
+        auto aligned = [&](const void* ptr, long long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((size_t)ld * oes) % 16 == 0; };
         const bool has_out1 = c.epi == EPI_BIAS_ACT_DZ || c.epi == EPI_BIAS_ACT_SE;
         const bool has_aux = has_out1 || c.epi == EPI_MUL_DACT || (c.epi == EPI_STORE && c.aux0 != nullptr);
-        tma_epi = make_map(&tm[2], odt, c.out0, c.N, c.M, c.ld_out0, 32, 32, oswz);
-        if (tma_epi && has_out1) tma_epi = make_map(&tm[3], odt, c.out1, c.N, c.M, c.ld_out1, 32, 32, oswz);
-        if (tma_epi && has_aux) tma_epi = make_map(&tm[4], odt, c.aux0, c.N, c.M, c.ld_aux0, 32, 32, oswz);
+        tma_epi = aligned(c.out0, c.ld_out0) && (!has_out1 || aligned(c.out1, c.ld_out1));
+        if (tma_epi && has_aux) tma_epi = make_map(&tm[2], c.io_bf16 ? 1 : 0, c.aux0, c.N, c.M, c.ld_aux0, 32, 32, c.io_bf16 ? SWZ_64 : SWZ_128);
     }
-
     GemmParams p{};
     p.M = c.M; p.N = c.N; p.K = c.K;
     p.num_m_tiles = (c.M + 127) / 128;
@@ -151,6 +151,10 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     p.io_bf16 = c.io_bf16;
     p.watchdog = watchdog_dev;
     p.tma_epi = tma_epi ? 1 : 0;
+    // fused column sums ride on the staged blocks of the TMA epilogue; tell the caller whether they were produced
+    p.colsum = (tma_epi && c.colsum_src != 0) ? c.colsum : nullptr;
+    p.colsum_src = c.colsum_src;
+    if (c.colsum_fused) *c.colsum_fused = p.colsum != nullptr ? 1 : 0;
     auto vec_ok = [&](const void* ptr, long long ld) {
         if (!ptr) return true;
         const int oes = c.io_bf16 ? 2 : 4;

@@ -57,6 +57,8 @@ struct GemmParams {
     const void* aux0; long long ld_aux0;
     const float* bias;
     float* loss;              // scalar accumulator (EPI_BIAS_ACT_SE)
+    float* colsum;            // optional [N] accumulator (pre-zeroed): column sums of out0 (colsum_src = 1) or out1 (= 2), TMA epilogue only
+    int colsum_src;
     int io_bf16;              // out0/out1/aux0 are bf16 (bf16 pipelines); 0 = fp32
     int vec_ok;               // 16-byte vector access legal for out0/out1/aux0
     int tma_epi;              // epilogue I/O goes through smem staging + TMA (tensor maps tmO0/tmO1/tmAux are valid)
@@ -80,8 +82,11 @@ struct GemmCfg {
     // epilogue staging: 32x32-element blocks (4 KiB fp32 / 2 KiB bf16) per epilogue warp, moved by TMA.
     // 1-pass: one block for the aux operand (prefetched one chunk ahead) + one for outputs; 3-pass: one shared block.
     static constexpr int EPI_WARPS = EPI_THREADS / 32;
-    static constexpr int EPI_NBUF = PASSES == 3 ? 1 : 2;
-    static constexpr int EPI_BYTES = EPI_WARPS * EPI_NBUF * 4096;
+    static constexpr int EPI_W = 32;                                       // columns per epilogue block
+    static constexpr int EPI_BLOCK_BYTES = 32 * EPI_W * (int)sizeof(T);    // 4096 (fp32, 128-byte rows) / 2048 (bf16, 64-byte rows)
+    static constexpr int EPI_NBUF = PASSES == 3 ? 1 : 2;                   // 1-pass: aux + out; 3-pass: one shared block
+    static constexpr int EPI_WARP_BYTES = EPI_NBUF * EPI_BLOCK_BYTES;
+    static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + EPI_BYTES + 1024 /*alignment slack*/;
     static_assert(BAR_BYTES <= 1024 && (3 * STAGES + 4 + EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier area");
     static_assert(PASSES == 1 || (PASSES == 3 && sizeof(T) == 4), "3-pass split is an fp32 technique");
@@ -98,13 +103,14 @@ __device__ __forceinline__ float act_deriv_from_out(int act, float a) {
     return 1.0f;
 }
 
-template <bool BF16>
-__device__ __forceinline__ void ld_row32(const void* base, long long ld, int row, int col, int N, bool vec, float (&x)[32]) {
+// W consecutive elements of one row, registers <-> global (direct epilogue path)
+template <bool BF16, int W>
+__device__ __forceinline__ void ld_row(const void* base, long long ld, int row, int col, int N, bool vec, float (&x)[W]) {
     if constexpr (BF16) {
         const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + (long long)row * ld + col;
-        if (vec && col + 32 <= N) {
+        if (vec && col + W <= N) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < W / 8; ++q) {
                 uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + q);
                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -115,30 +121,30 @@ __device__ __forceinline__ void ld_row32(const void* base, long long ld, int row
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) x[e] = (col + e < N) ? __bfloat162float(p[e]) : 0.f;
+            for (int e = 0; e < W; ++e) x[e] = (col + e < N) ? __bfloat162float(p[e]) : 0.f;
         }
     } else {
         const float* p = reinterpret_cast<const float*>(base) + (long long)row * ld + col;
-        if (vec && col + 32 <= N) {
+        if (vec && col + W <= N) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < W / 4; ++q) {
                 float4 f = __ldg(reinterpret_cast<const float4*>(p) + q);
                 x[q * 4] = f.x; x[q * 4 + 1] = f.y; x[q * 4 + 2] = f.z; x[q * 4 + 3] = f.w;
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) x[e] = (col + e < N) ? p[e] : 0.f;
+            for (int e = 0; e < W; ++e) x[e] = (col + e < N) ? p[e] : 0.f;
         }
     }
 }
 
-template <bool BF16>
-__device__ __forceinline__ void st_row32(void* base, long long ld, int row, int col, int N, bool vec, const float (&x)[32]) {
+template <bool BF16, int W>
+__device__ __forceinline__ void st_row(void* base, long long ld, int row, int col, int N, bool vec, const float (&x)[W]) {
     if constexpr (BF16) {
         __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + (long long)row * ld + col;
-        if (vec && col + 32 <= N) {
+        if (vec && col + W <= N) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < W / 8; ++q) {
                 uint4 u;
                 __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
@@ -147,17 +153,17 @@ __device__ __forceinline__ void st_row32(void* base, long long ld, int row, int 
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) if (col + e < N) p[e] = __float2bfloat16_rn(x[e]);
+            for (int e = 0; e < W; ++e) if (col + e < N) p[e] = __float2bfloat16_rn(x[e]);
         }
     } else {
         float* p = reinterpret_cast<float*>(base) + (long long)row * ld + col;
-        if (vec && col + 32 <= N) {
+        if (vec && col + W <= N) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
+            for (int q = 0; q < W / 4; ++q)
                 reinterpret_cast<float4*>(p)[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
         } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) if (col + e < N) p[e] = x[e];
+            for (int e = 0; e < W; ++e) if (col + e < N) p[e] = x[e];
         }
     }
 }
@@ -168,33 +174,42 @@ __device__ __forceinline__ bool epi_has_aux(const GemmParams& p) {
 }
 __device__ __forceinline__ bool epi_has_out1(const GemmParams& p) { return p.epi == EPI_BIAS_ACT_DZ || p.epi == EPI_BIAS_ACT_SE; }
 
-// Math for 32 consecutive columns [col, col+32) of one output row (every epilogue except EPI_ATOMIC).
+// Math for W consecutive columns [col, col+W) of one output row (every epilogue except EPI_ATOMIC).
 //   in : v = accumulators, x = aux values (if epi_has_aux)        out: v = out0 values, x = out1 values (if epi_has_out1)
-__device__ __forceinline__ void epi_math32(const GemmParams& p, bool row_ok, int col, float (&v)[32], float (&x)[32], float& loss_acc) {
+template <int W>
+__device__ __forceinline__ void epi_math(const GemmParams& p, bool row_ok, int col, float (&v)[W], float (&x)[W], float& loss_acc) {
     switch (p.epi) {
         case EPI_STORE: {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] *= p.alpha;
+            for (int e = 0; e < W; ++e) v[e] *= p.alpha;
             if (p.aux0 != nullptr) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = fmaf(p.beta, x[e], v[e]);
+                for (int e = 0; e < W; ++e) v[e] = fmaf(p.beta, x[e], v[e]);
             }
         } break;
         case EPI_BIAS_ACT:
         case EPI_BIAS_ACT_DZ:
         case EPI_BIAS_ACT_SE: {
             if (p.bias != nullptr) {
+                if (col + W <= p.N && (reinterpret_cast<uintptr_t>(p.bias + col) & 15) == 0) {   // warp-uniform broadcast loads
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
+                    for (int g = 0; g < W / 4; ++g) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + g);
+                        v[g * 4] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < W; ++e) v[e] += (col + e < p.N) ? __ldg(p.bias + col + e) : 0.f;
+                }
             }
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = act_apply(p.act, v[e]);
+            for (int e = 0; e < W; ++e) v[e] = act_apply(p.act, v[e]);
             if (p.epi == EPI_BIAS_ACT_DZ) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) x[e] = x[e] * act_deriv_from_out(p.act, v[e]);
+                for (int e = 0; e < W; ++e) x[e] = x[e] * act_deriv_from_out(p.act, v[e]);
             } else if (p.epi == EPI_BIAS_ACT_SE) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
+                for (int e = 0; e < W; ++e) {
                     const float d = (row_ok && col + e < p.N) ? x[e] - v[e] : 0.f;   // squaredError: NeuralNet.hs:61-68
                     loss_acc = fmaf(d, d, loss_acc);
                     x[e] = -2.0f * d * act_deriv_from_out(p.act, v[e]);
@@ -203,7 +218,7 @@ __device__ __forceinline__ void epi_math32(const GemmParams& p, bool row_ok, int
         } break;
         case EPI_MUL_DACT: {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] *= act_deriv_from_out(p.act, x[e]);
+            for (int e = 0; e < W; ++e) v[e] *= act_deriv_from_out(p.act, x[e]);
         } break;
         default: break;
     }
@@ -211,137 +226,177 @@ __device__ __forceinline__ void epi_math32(const GemmParams& p, bool row_ok, int
 
 // Direct (register <-> global) epilogue: used for EPI_ATOMIC and whenever the outputs cannot be described by TMA
 // tensor maps (unaligned base / leading dimension).  Row-per-thread accesses: correct everywhere, slow.
-__device__ __forceinline__ void epi_direct32(const GemmParams& p, int row, int col, bool vec, float (&v)[32], float& loss_acc) {
+template <int W>
+__device__ __forceinline__ void epi_direct(const GemmParams& p, int row, int col, bool vec, float (&v)[W], float& loss_acc) {
     const bool bf = p.io_bf16 != 0;
     if (p.epi == EPI_ATOMIC) {
         float* o = reinterpret_cast<float*>(p.out0) + (long long)row * p.ld_out0 + col;
-        if (vec && col + 32 <= p.N) {
+        if (vec && col + W <= p.N) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
+            for (int g = 0; g < W / 4; ++g)
                 ptx::red_add_v4(o + g * 4, p.alpha * v[g * 4], p.alpha * v[g * 4 + 1], p.alpha * v[g * 4 + 2], p.alpha * v[g * 4 + 3]);
         } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) if (col + e < p.N) atomicAdd(o + e, p.alpha * v[e]);
+            for (int e = 0; e < W; ++e) if (col + e < p.N) atomicAdd(o + e, p.alpha * v[e]);
         }
         return;
     }
-    float x[32];
+    float x[W];
     if (epi_has_aux(p)) {
-        if (bf) ld_row32<true>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
-        else ld_row32<false>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+        if (bf) ld_row<true, W>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
+        else ld_row<false, W>(p.aux0, p.ld_aux0, row, col, p.N, vec, x);
     }
-    epi_math32(p, true, col, v, x, loss_acc);
-    if (bf) st_row32<true>(p.out0, p.ld_out0, row, col, p.N, vec, v);
-    else st_row32<false>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+    epi_math<W>(p, true, col, v, x, loss_acc);
+    if (bf) st_row<true, W>(p.out0, p.ld_out0, row, col, p.N, vec, v);
+    else st_row<false, W>(p.out0, p.ld_out0, row, col, p.N, vec, v);
     if (epi_has_out1(p)) {
-        if (bf) st_row32<true>(p.out1, p.ld_out1, row, col, p.N, vec, x);
-        else st_row32<false>(p.out1, p.ld_out1, row, col, p.N, vec, x);
+        if (bf) st_row<true, W>(p.out1, p.ld_out1, row, col, p.N, vec, x);
+        else st_row<false, W>(p.out1, p.ld_out1, row, col, p.N, vec, x);
     }
 }
 
-// Staging blocks are 32 rows x 32 elements, laid out the way the TMA swizzle modes expect so that both the thread side
-// (lane = row, 16-byte accesses) and the TMA side are bank-conflict free:
-//   fp32: 128-byte rows, SWIZZLE_128B: 16B chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
-//   bf16:  64-byte rows, SWIZZLE_64B : 16B chunk j of row r lives at r*64  + ((j ^ ((r >> 1) & 3)) << 4)
-__device__ __forceinline__ void stage_read_row(const uint8_t* buf, bool bf, int r, float (&x)[32]) {
-    if (bf) {
+// Staging blocks are 32 rows x W elements of IO, rows of 64 or 128 bytes, laid out the way the TMA swizzle modes expect
+// so that both the thread side (lane = row, 16-byte accesses) and the TMA side are bank-conflict free:
+//   128-byte rows, SWIZZLE_128B: 16B chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
+//    64-byte rows, SWIZZLE_64B : 16B chunk j of row r lives at r*64  + ((j ^ ((r >> 1) & 3)) << 4)
+template <int ROWB> __device__ __forceinline__ int stage_off(int r, int j) {
+    if constexpr (ROWB == 128) return r * 128 + ((j ^ (r & 7)) << 4);
+    else return r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
+}
+template <typename IO, int W>
+__device__ __forceinline__ void stage_read_row(uint32_t buf, int r, float (&x)[W]) {
+    constexpr int ROWB = W * (int)sizeof(IO);
+    static_assert(ROWB == 64 || ROWB == 128, "staging rows are 64 or 128 bytes");
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(buf + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+    for (int j = 0; j < ROWB / 16; ++j) {
+        const uint4 u = ptx::lds128(buf + stage_off<ROWB>(r, j));
+        if constexpr (sizeof(IO) == 2) {
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float2 f = __bfloat1622float2(h[e]);
                 x[j * 8 + e * 2] = f.x; x[j * 8 + e * 2 + 1] = f.y;
             }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 f = *reinterpret_cast<const float4*>(buf + r * 128 + ((j ^ (r & 7)) << 4));
-            x[j * 4] = f.x; x[j * 4 + 1] = f.y; x[j * 4 + 2] = f.z; x[j * 4 + 3] = f.w;
+        } else {
+            x[j * 4] = __uint_as_float(u.x); x[j * 4 + 1] = __uint_as_float(u.y); x[j * 4 + 2] = __uint_as_float(u.z); x[j * 4 + 3] = __uint_as_float(u.w);
         }
     }
 }
-__device__ __forceinline__ void stage_write_row(uint8_t* buf, bool bf, int r, const float (&x)[32]) {
-    if (bf) {
+template <typename IO, int W>
+__device__ __forceinline__ void stage_write_row(uint32_t buf, int r, const float (&x)[W]) {
+    constexpr int ROWB = W * (int)sizeof(IO);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 u;
+    for (int j = 0; j < ROWB / 16; ++j) {
+        uint4 u;
+        if constexpr (sizeof(IO) == 2) {
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(x[j * 8 + e * 2], x[j * 8 + e * 2 + 1]);
-            *reinterpret_cast<uint4*>(buf + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = u;
+        } else {
+            u = make_uint4(__float_as_uint(x[j * 4]), __float_as_uint(x[j * 4 + 1]), __float_as_uint(x[j * 4 + 2]), __float_as_uint(x[j * 4 + 3]));
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(buf + r * 128 + ((j ^ (r & 7)) << 4)) = make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
+        ptx::sts128(buf + stage_off<ROWB>(r, j), u);
     }
 }
-
-// Per-warp state of the TMA epilogue.
-struct EpiWarp {
-    uint8_t* aux_buf;      // staging block for the aux operand
-    uint8_t* out_buf;      // staging block for out0 / out1 (== aux_buf when the kernel has one block per warp)
-    uint64_t* aux_bar;     // mbarrier the aux TMA load completes on
-    uint32_t aux_count;    // aux loads consumed so far (parity of the next wait)
-    bool prefetched;       // the aux block of the chunk about to be processed is already in flight
-};
-
-__device__ __forceinline__ void epi_issue_aux(const GemmParams& p, const CUtensorMap* tmAux, EpiWarp& w, int row0, int col) {
-    ptx::mbar_arrive_expect_tx(w.aux_bar, p.io_bf16 ? 2048u : 4096u);
-    ptx::tma_load_2d(w.aux_buf, tmAux, w.aux_bar, col, row0);
+// Column sums of a staged 32 x W block, added into colsum[col .. col+W) with one red per column (db = sum_s dZ[s,:]).
+template <typename IO, int W>
+__device__ __forceinline__ void stage_colsum(uint32_t buf, int lane, int col, int N, float* colsum) {
+    constexpr int ROWB = W * (int)sizeof(IO);
+    constexpr int EPC = 16 / (int)sizeof(IO);          // elements per 16-byte chunk
+    static_assert(W == 32, "one column per lane");
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+        const uint32_t a = buf + stage_off<ROWB>(r, lane / EPC) + (lane % EPC) * (int)sizeof(IO);
+        if constexpr (sizeof(IO) == 2) s += __uint_as_float(static_cast<uint32_t>(ptx::lds16(a)) << 16);
+        else s += ptx::lds32f(a);
+    }
+    if (col + lane < N) atomicAdd(colsum + col + lane, s);
 }
 
-// One 32x32 block of the output tile, warp-collective: rows row0..row0+31 (lane = row), columns col..col+31.
-//   v: this lane's accumulators.  next_col >= 0: column of the next block this warp will process in the same rows (its aux
-//   block is prefetched when the kernel has a separate aux staging block).
-__device__ __forceinline__ void epi_tma_block(const GemmParams& p, const CUtensorMap* tmO0, const CUtensorMap* tmO1, const CUtensorMap* tmAux,
-                                              EpiWarp& w, int lane, int row0, int col, int next_col, float (&v)[32], float& loss_acc,
-                                              volatile unsigned int* wd) {
-    const bool bf = p.io_bf16 != 0;
-    const bool has_aux = epi_has_aux(p), has_out1 = epi_has_out1(p);
-    const bool shared_buf = (w.aux_buf == w.out_buf);
-    float x[32];
-    if (has_aux) {
-        if (!w.prefetched) {
-            if (lane == 0) {
-                if (shared_buf) ptx::tma_store_wait_read();   // a store may still be reading the shared block
-                epi_issue_aux(p, tmAux, w, row0, col);
+// Coalesced copy of a staged 32 x W block to global memory: consecutive lanes take consecutive 16-byte chunks of a row, so a
+// warp instruction writes whole 64/128-byte row segments (4-8 L1 wavefronts instead of the 32 of row-per-thread stores).
+// Plain st.global: fire-and-forget, no completion to wait for before the staging block is reused.
+template <typename IO, int W>
+__device__ __forceinline__ void stage_store_global(uint32_t buf, int lane, void* base, long long ld, int row0, int col, int M, int N) {
+    constexpr int ROWB = W * (int)sizeof(IO);
+    constexpr int CPR = ROWB / 16;                 // 16-byte chunks per row
+    constexpr int EPC = 16 / (int)sizeof(IO);      // elements per chunk
+    const int j = lane % CPR, c = col + j * EPC;
+    IO* g0 = reinterpret_cast<IO*>(base) + (long long)(row0 + lane / CPR) * ld + c;
+    if (c >= N) return;
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) {
+        const int r = lane / CPR + k * (32 / CPR);
+        if (row0 + r < M) {
+            const uint4 u = ptx::lds128(buf + stage_off<ROWB>(r, j));
+            IO* g = g0 + (long long)k * (32 / CPR) * ld;
+            if (c + EPC <= N) {
+                *reinterpret_cast<uint4*>(g) = u;
+            } else {
+                const IO* e = reinterpret_cast<const IO*>(&u);
+#pragma unroll
+                for (int i = 0; i < EPC; ++i) if (c + i < N) g[i] = e[i];
             }
         }
-        ptx::mbar_wait(w.aux_bar, w.aux_count & 1, wd, 0x600);
-        ++w.aux_count;
-        stage_read_row(w.aux_buf, bf, lane, x);
-        __syncwarp();
-        w.prefetched = false;
-        if (!shared_buf && next_col >= 0) {
-            if (lane == 0) epi_issue_aux(p, tmAux, w, row0, next_col);
-            w.prefetched = true;
-        }
     }
-    epi_math32(p, row0 + lane < p.M, col, v, x, loss_acc);
-    if (lane == 0) ptx::tma_store_wait_read();
+}
+
+// Per-warp state of the staged epilogue.  The aux operand (dA / target / previous activation / C) arrives by TMA into
+// `aux_buf`; outputs are transposed through `out_buf` (== aux_buf in the 3-pass kernel, which has one block per warp).
+struct EpiWarp {
+    uint32_t aux_buf;      // shared-window byte addresses
+    uint32_t out_buf;
+    uint64_t* aux_bar;     // mbarrier the aux TMA load completes on
+    uint32_t consumed;     // aux loads consumed so far (parity of the next wait)
+    bool in_flight;        // the aux block of the block about to be processed has already been requested
+};
+
+template <typename IO, int W>
+__device__ __forceinline__ void epi_issue_aux(const CUtensorMap* tmAux, EpiWarp& w, int lane, int row0, int col) {
+    if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(w.aux_bar, 32u * W * (uint32_t)sizeof(IO));
+        ptx::tma_load_2d_s(w.aux_buf, tmAux, w.aux_bar, col, row0);
+    }
+    w.in_flight = true;
+}
+
+// One 32 x W block of the output tile, warp-collective: rows row0..row0+31 (lane = row), columns col..col+W-1.
+//   v: this lane's accumulators.  next_col >= 0: column of the next block this warp will process in the same rows; when the
+//   aux block is separate from the output block its aux operand is requested as soon as this block's has been read.
+template <typename IO, int W, bool SHARED>
+__device__ __forceinline__ void epi_block(const GemmParams& p, const CUtensorMap* tmAux, EpiWarp& w, int lane, int row0, int col, int next_col,
+                                          float (&v)[W], float& loss_acc, volatile unsigned int* wd) {
+    const bool has_aux = epi_has_aux(p), has_out1 = epi_has_out1(p);
+    float x[W];
+    if (has_aux) {
+        if (!w.in_flight) epi_issue_aux<IO, W>(tmAux, w, lane, row0, col);
+        ptx::mbar_wait(w.aux_bar, w.consumed & 1, wd, 0x600);
+        ++w.consumed;
+        stage_read_row<IO, W>(w.aux_buf, lane, x);
+        __syncwarp();
+        w.in_flight = false;
+        if (!SHARED && next_col >= 0) epi_issue_aux<IO, W>(tmAux, w, lane, row0, next_col);
+    }
+    epi_math<W>(p, row0 + lane < p.M, col, v, x, loss_acc);
+    stage_write_row<IO, W>(w.out_buf, lane, v);
     __syncwarp();
-    stage_write_row(w.out_buf, bf, lane, v);
-    ptx::fence_proxy_async_smem();
+    stage_store_global<IO, W>(w.out_buf, lane, p.out0, p.ld_out0, row0, col, p.M, p.N);
+    if (p.colsum != nullptr && p.colsum_src == 1) stage_colsum<IO, W>(w.out_buf, lane, col, p.N, p.colsum);
     __syncwarp();
-    if (lane == 0) { ptx::tma_store_2d(tmO0, w.out_buf, col, row0); ptx::tma_store_commit(); }
     if (has_out1) {
-        if (lane == 0) ptx::tma_store_wait_read();
+        stage_write_row<IO, W>(w.out_buf, lane, x);
         __syncwarp();
-        stage_write_row(w.out_buf, bf, lane, x);
-        ptx::fence_proxy_async_smem();
+        stage_store_global<IO, W>(w.out_buf, lane, p.out1, p.ld_out1, row0, col, p.M, p.N);
+        if (p.colsum != nullptr && p.colsum_src == 2) stage_colsum<IO, W>(w.out_buf, lane, col, p.N, p.colsum);
         __syncwarp();
-        if (lane == 0) { ptx::tma_store_2d(tmO1, w.out_buf, col, row0); ptx::tma_store_commit(); }
     }
 }
 
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
 __global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES>::NUM_THREADS), 1)
-gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
-                 const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAux,
+                 const GemmParams p) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES>;
     constexpr bool kBF16 = sizeof(T) == 2;
     constexpr bool kChunked = PASSES == 3;   // TMEM holds one chunk; the running sum lives in epilogue registers
@@ -368,11 +423,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
-        if (p.tma_epi) {
-            ptx::prefetch_tensormap(&tmO0);
-            if (epi_has_out1(p)) ptx::prefetch_tensormap(&tmO1);
-            if (epi_has_aux(p)) ptx::prefetch_tensormap(&tmAux);
-        }
+        if (p.tma_epi && epi_has_aux(p)) ptx::prefetch_tensormap(&tmAux);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -483,13 +534,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (!kChunked) {
         // ===================================================== epilogue, 1-pass: warps 4-7, one TMEM buffer per work item
+        constexpr int W = Cfg::EPI_W;
         const int q = warp & 3;   // TMEM lane quarter this warp may read
         const bool vec = p.vec_ok != 0;
         const bool tma = p.tma_epi != 0;
         EpiWarp ew;
-        ew.aux_buf = epi_smem + (warp - 4) * (Cfg::EPI_NBUF * 4096);
-        ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * 4096;
-        ew.aux_bar = &epi_bar[warp - 4]; ew.aux_count = 0; ew.prefetched = false;
+        ew.aux_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
+        ew.out_buf = ew.aux_buf + Cfg::EPI_BLOCK_BYTES;
+        ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false;
         int it = 0;
         float loss_acc = 0.f;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
@@ -498,31 +550,29 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
-            const int ncols = min(BN, p.N - n0);                  // valid columns of this tile (warp-uniform)
-            const int nblk = row0 < p.M ? (ncols + 31) / 32 : 0;  // 32-column blocks this warp owns in this tile
-            if (tma && nblk > 0 && epi_has_aux(p)) {              // the first aux block does not depend on the accumulators
-                if (lane == 0) epi_issue_aux(p, &tmAux, ew, row0, n0);
-                ew.prefetched = true;
-            }
+            const int ncols = min(BN, p.N - n0);                        // valid columns of this tile (warp-uniform)
+            const int nblk = row0 < p.M ? (ncols + W - 1) / W : 0;      // W-column blocks this warp owns in this tile
+            if (tma && nblk > 0 && epi_has_aux(p))                      // the first aux block does not depend on the accumulators
+                epi_issue_aux<T, W>(&tmAux, ew, lane, row0, n0);
             ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
             ptx::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < nblk; ++c) {
-                uint32_t raw[32];
-                ptx::tmem_ld_32x32b_x32(t_row + c * 32, raw);
+                uint32_t raw[W];
+                if constexpr (W == 32) ptx::tmem_ld_32x32b_x32(t_row + c * W, raw);
+                else ptx::tmem_ld_32x32b_x16(t_row + c * W, raw);
                 ptx::tmem_ld_wait();
-                const int col = n0 + c * 32;
-                float v[32];
+                const int col = n0 + c * W;
+                float v[W];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
-                if (tma) epi_tma_block(p, &tmO0, &tmO1, &tmAux, ew, lane, row0, col, c + 1 < nblk ? col + 32 : -1, v, loss_acc, wd);
-                else if (row < p.M) epi_direct32(p, row, col, vec, v, loss_acc);
+                for (int e = 0; e < W; ++e) v[e] = __uint_as_float(raw[e]);
+                if (tma) epi_block<T, W, false>(p, &tmAux, ew, lane, row0, col, c + 1 < nblk ? col + W : -1, v, loss_acc, wd);
+                else if (row < p.M) epi_direct<W>(p, row, col, vec, v, loss_acc);
             }
             ptx::tcgen05_fence_before();
             ptx::mbar_arrive(&tmem_empty[acc]);
         }
-        if (tma && lane == 0) ptx::tma_store_wait_all();
         if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
@@ -537,9 +587,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool vec = p.vec_ok != 0;
         const bool tma = p.tma_epi != 0;
         EpiWarp ew;
-        ew.aux_buf = epi_smem + (warp - 4) * (Cfg::EPI_NBUF * 4096);
-        ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * 4096;
-        ew.aux_bar = &epi_bar[warp - 4]; ew.aux_count = 0; ew.prefetched = false;
+        ew.aux_buf = ew.out_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
+        ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false;
         int it = 0;
         float loss_acc = 0.f;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -569,20 +618,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
             if (row0 < p.M) {
-#pragma unroll
+                // ONE copy of the block code (the fused epilogue is large; unrolled four times it thrashes the instruction
+                // cache): always process sum[0..31], then rotate the register accumulators down by one block.
+#pragma unroll 1
                 for (int c = 0; c < HC / 32; ++c) {
                     const int col = n0 + half * HC + c * 32;
-                    if (col < p.N) {
-                        float v[32];
+                    float v[32];
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = sum[c * 32 + e];
-                        if (tma) epi_tma_block(p, &tmO0, &tmO1, &tmAux, ew, lane, row0, col, -1, v, loss_acc, wd);
-                        else if (row < p.M) epi_direct32(p, row, col, vec, v, loss_acc);
+                    for (int e = 0; e < 32; ++e) v[e] = sum[e];
+#pragma unroll
+                    for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];
+                    if (col < p.N) {
+                        if (tma) epi_block<float, 32, true>(p, &tmAux, ew, lane, row0, col, -1, v, loss_acc, wd);
+                        else if (row < p.M) epi_direct<32>(p, row, col, vec, v, loss_acc);
                     }
                 }
             }
         }
-        if (tma && lane == 0) ptx::tma_store_wait_all();
         if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
@@ -599,19 +651,19 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
             for (int kb = kb0; kb < kb1; ++kb) {
                 ptx::mbar_wait(&full_bar[s], ph, wd, 0x500 + s);
-                float4* hi = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + Cfg::RAW_BYTES);
+                const uint32_t hi = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t lo = hi + Cfg::RAW_BYTES;
 #pragma unroll 4
                 for (int i = t; i < Cfg::RAW_BYTES / 16; i += 128) {
                     // kind::tf32 TRUNCATES fp32 operands (measured: tools/gemm_probe, ref_mode=1), so the raw tile already
                     // acts as hi = trunc_tf32(x); only lo = x - hi (exact in fp32) has to be materialised.
-                    const float4 x = hi[i];
-                    float4 l;
-                    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-                    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-                    l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-                    l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-                    lo[i] = l;
+                    const uint4 x = ptx::lds128(hi + i * 16);
+                    uint4 l;
+                    l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(x.x & 0xffffe000u));
+                    l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(x.y & 0xffffe000u));
+                    l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(x.z & 0xffffe000u));
+                    l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(x.w & 0xffffe000u));
+                    ptx::sts128(lo + i * 16, l);
                 }
                 ptx::fence_proxy_async_smem();
                 ptx::mbar_arrive(&ready_bar[s]);

@@ -23,6 +23,9 @@ struct GemmCall {
     int split_k;    // 0 = choose automatically (only EPI_ATOMIC may split)
     int block_n;    // 0 = choose automatically, else 128 or 256
     int max_ctas;   // 0 = number of SMs
+    float* colsum;         // optional [N] fp32 accumulator, PRE-ZEROED by the caller: column sums of out0 (colsum_src 1) / out1 (2)
+    int colsum_src;        // 0 = none
+    int* colsum_fused;     // out: set to 1 if the kernel produced the column sums (TMA epilogue), else 0 (caller reduces separately)
     int no_tma_epilogue;   // 1 = force the direct register<->global epilogue (bring-up / A-B comparison)
     int chunk_kb;   // 3-pass only: k-blocks per TMEM chunk before promotion to fp32 registers (0 = default 4)
     const char* tag;   // profiling label (tops_profile_*), may be NULL
