@@ -70,6 +70,11 @@ cudaError_t launch_major(int bn, int passes, const CUtensorMap* tm, const GemmPa
             return launch_one<T, MA, MB, 256, 2, 3>(tm, p, grid, st);
         }
     }
+    // fp32 1-pass: one stage fewer than fits, so that each epilogue warp gets separate aux and output staging blocks
+    if constexpr (sizeof(T) == 4) {
+        if (bn == 128) return launch_one<T, MA, MB, 128, 5, 1>(tm, p, grid, st);
+        return launch_one<T, MA, MB, 256, 3, 1>(tm, p, grid, st);
+    }
     if (bn == 128) return launch_one<T, MA, MB, 128, 6, 1>(tm, p, grid, st);
     return launch_one<T, MA, MB, 256, 4, 1>(tm, p, grid, st);
 }

@@ -75,8 +75,8 @@ struct GemmCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (PASSES == 3 ? 2 : 1);
-    static constexpr int NUM_THREADS = PASSES == 3 ? 512 : 256;
-    static constexpr int EPI_THREADS = PASSES == 3 ? 256 : 128;
+    static constexpr int NUM_THREADS = PASSES == 3 ? 512 : 384;
+    static constexpr int EPI_THREADS = 256;                 // 8 epilogue warps: 2 per TMEM lane quarter, each owning half of the tile's columns
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 512;
     // epilogue staging: 32x32-element blocks (4 KiB fp32 / 2 KiB bf16) per epilogue warp, moved by TMA.
@@ -84,7 +84,10 @@ struct GemmCfg {
     static constexpr int EPI_WARPS = EPI_THREADS / 32;
     static constexpr int EPI_W = 32;                                       // columns per epilogue block
     static constexpr int EPI_BLOCK_BYTES = 32 * EPI_W * (int)sizeof(T);    // 4096 (fp32, 128-byte rows) / 2048 (bf16, 64-byte rows)
-    static constexpr int EPI_NBUF = PASSES == 3 ? 1 : 2;                   // 1-pass: aux + out; 3-pass: one shared block
+    // two blocks per warp (aux operand prefetched while the previous block is written out) when the pipeline stages leave
+    // room for them, otherwise one block shared by the aux operand and the outputs
+    static constexpr int EPI_NBUF = (232448 - STAGES * STAGE_BYTES - 2048 >= EPI_WARPS * 2 * EPI_BLOCK_BYTES) ? 2 : 1;
+    static constexpr bool EPI_SHARED = EPI_NBUF == 1;
     static constexpr int EPI_WARP_BYTES = EPI_NBUF * EPI_BLOCK_BYTES;
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + EPI_BYTES + 1024 /*alignment slack*/;
@@ -95,7 +98,12 @@ struct GemmCfg {
 };
 
 __device__ __forceinline__ float act_apply(int act, float z) {
-    if (act == ACT_LOGISTIC) return __fdividef(1.0f, 1.0f + __expf(-z));   // NeuralNet.hs:42-44
+    if (act == ACT_LOGISTIC) {                                             // 1 / (1 + exp(-z)), NeuralNet.hs:42-44
+        float e, r;                                                        // ex2.approx / rcp.approx: 2 MUFU + FMUL + FADD, rel. error ~2e-7
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        return r;
+    }
     return z;
 }
 __device__ __forceinline__ float act_deriv_from_out(int act, float a) {
@@ -305,12 +313,18 @@ __device__ __forceinline__ void stage_colsum(uint32_t buf, int lane, int col, in
     constexpr int EPC = 16 / (int)sizeof(IO);          // elements per 16-byte chunk
     static_assert(W == 32, "one column per lane");
     float s = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-        const uint32_t a = buf + stage_off<ROWB>(r, lane / EPC) + (lane % EPC) * (int)sizeof(IO);
-        if constexpr (sizeof(IO) == 2) s += __uint_as_float(static_cast<uint32_t>(ptx::lds16(a)) << 16);
-        else s += ptx::lds32f(a);
+    constexpr int NSW = ROWB == 128 ? 8 : 4;           // distinct swizzle patterns; rows r and r + period share one
+    constexpr int PERIOD = 8;                          // stage_off(r + 8, j) == stage_off(r, j) + 8 * ROWB for both layouts
+#pragma unroll
+    for (int k = 0; k < PERIOD; ++k) {
+        const uint32_t a = buf + stage_off<ROWB>(k, lane / EPC) + (lane % EPC) * (int)sizeof(IO);
+#pragma unroll
+        for (int m = 0; m < 32 / PERIOD; ++m) {
+            if constexpr (sizeof(IO) == 2) s += __uint_as_float(static_cast<uint32_t>(ptx::lds16(a + m * PERIOD * ROWB)) << 16);
+            else s += ptx::lds32f(a + m * PERIOD * ROWB);
+        }
     }
+    (void)NSW;
     if (col + lane < N) atomicAdd(colsum + col + lane, s);
 }
 
@@ -453,6 +467,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp < 4) {
         if constexpr (kChunked) ptx::setmaxnreg_dec<48>();
+        else ptx::setmaxnreg_dec<56>();
         if (warp == 0 && lane == 0) {
             // ===================================================== TMA producer
             int s = 0; uint32_t ph = 0;
@@ -533,41 +548,43 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (!kChunked) {
-        // ===================================================== epilogue, 1-pass: warps 4-7, one TMEM buffer per work item
+        // ===================================================== epilogue, 1-pass: warps 4-11, one TMEM buffer per work item
+        ptx::setmaxnreg_inc<224>();
         constexpr int W = Cfg::EPI_W;
-        const int q = warp & 3;   // TMEM lane quarter this warp may read
+        constexpr int HC = BN / 2;            // columns per warp: half of the tile
+        const int q = warp & 3;               // TMEM lane quarter this warp may read (hardware rule: lanes 32*(warp%4)..+31)
+        const int half = (warp - 4) >> 2;     // column half
         const bool vec = p.vec_ok != 0;
         const bool tma = p.tma_epi != 0;
         EpiWarp ew;
         ew.aux_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
-        ew.out_buf = ew.aux_buf + Cfg::EPI_BLOCK_BYTES;
+        ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * Cfg::EPI_BLOCK_BYTES;
         ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false;
         int it = 0;
         float loss_acc = 0.f;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
             const int tile = w % num_tiles;
-            const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+            const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN + half * HC;
             const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
-            const int ncols = min(BN, p.N - n0);                        // valid columns of this tile (warp-uniform)
-            const int nblk = row0 < p.M ? (ncols + W - 1) / W : 0;      // W-column blocks this warp owns in this tile
-            if (tma && nblk > 0 && epi_has_aux(p))                      // the first aux block does not depend on the accumulators
+            const int ncols = min(HC, p.N - n0);                              // valid columns of this warp's half (may be <= 0)
+            const int nblk = (row0 < p.M && ncols > 0) ? (ncols + W - 1) / W : 0;   // W-column blocks this warp owns in this tile
+            if (tma && nblk > 0 && epi_has_aux(p))                            // the first aux block does not depend on the accumulators
                 epi_issue_aux<T, W>(&tmAux, ew, lane, row0, n0);
             ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
             ptx::tcgen05_fence_after();
-            const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+            const uint32_t t_row = tmem_base + acc * BN + half * HC + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < nblk; ++c) {
                 uint32_t raw[W];
-                if constexpr (W == 32) ptx::tmem_ld_32x32b_x32(t_row + c * W, raw);
-                else ptx::tmem_ld_32x32b_x16(t_row + c * W, raw);
+                ptx::tmem_ld_32x32b_x32(t_row + c * W, raw);
                 ptx::tmem_ld_wait();
                 const int col = n0 + c * W;
                 float v[W];
 #pragma unroll
                 for (int e = 0; e < W; ++e) v[e] = __uint_as_float(raw[e]);
-                if (tma) epi_block<T, W, false>(p, &tmAux, ew, lane, row0, col, c + 1 < nblk ? col + W : -1, v, loss_acc, wd);
+                if (tma) epi_block<T, W, Cfg::EPI_SHARED>(p, &tmAux, ew, lane, row0, col, c + 1 < nblk ? col + W : -1, v, loss_acc, wd);
                 else if (row < p.M) epi_direct<W>(p, row, col, vec, v, loss_acc);
             }
             ptx::tcgen05_fence_before();
@@ -587,7 +604,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool vec = p.vec_ok != 0;
         const bool tma = p.tma_epi != 0;
         EpiWarp ew;
-        ew.aux_buf = ew.out_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
+        ew.aux_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
+        ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * Cfg::EPI_BLOCK_BYTES;
         ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false;
         int it = 0;
         float loss_acc = 0.f;
@@ -596,6 +614,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+            if (tma && epi_has_aux(p) && m0 + q * 32 < p.M && n0 + half * HC < p.N)   // first aux block: requested before the K loop
+                epi_issue_aux<float, 32>(&tmAux, ew, lane, m0 + q * 32, n0 + half * HC);
             float sum[HC];
 #pragma unroll
             for (int e = 0; e < HC; ++e) sum[e] = 0.f;
@@ -629,7 +649,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];
                     if (col < p.N) {
-                        if (tma) epi_block<float, 32, true>(p, &tmAux, ew, lane, row0, col, -1, v, loss_acc, wd);
+                        if (tma) epi_block<float, 32, Cfg::EPI_SHARED>(p, &tmAux, ew, lane, row0, col, (c + 1 < HC / 32 && col + 32 < p.N) ? col + 32 : -1, v, loss_acc, wd);
                         else if (row < p.M) epi_direct<32>(p, row, col, vec, v, loss_acc);
                     }
                 }
