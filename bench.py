@@ -280,7 +280,7 @@ def main():
 
         def e2e_step():
             g = nn.fflayer_fwd_grad_host(ctx, Xn, W, b, dAn, grads_out=gn, allreduce=(lambda: dp.allreduce_sum_(packed_t)) if world > 1 else None,
-                                         workspace=(X, dA, A, dX, packed))
+                                         workspace=(A, dX, packed))
             return g
         for _ in range(2):
             e2e_step()

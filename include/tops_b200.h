@@ -158,6 +158,13 @@ int tops_fflayer_grad(tops_ctx*, const tops_buf* X, const tops_buf* W, const top
 /* forward + VJP in one call; the activation and dZ never leave the device and are produced by one GEMM epilogue */
 int tops_fflayer_fwd_grad(tops_ctx*, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act,
                           const tops_buf* dA, tops_buf** A, tops_buf** dX, tops_buf** dW, tops_buf** db);
+/* The same forward + VJP with the batch in HOST memory (the reference builds tensors from Haskell lists with `fromList` and reads
+ * results with `toList`, Tensor.hs:187-273): X_host[B,i] and dA_host[B,o] are row-major fp32 host arrays (pinned for full PCIe
+ * rate), cut into `n_chunks` row chunks (0 = default 8) whose host->device copies overlap the GEMMs of the previous chunk.
+ * `grads` receives the packed device buffer [dW (o*i) || db (o)], summed over the batch; if `grads_host` is non-NULL the packed
+ * gradient is also copied there and the call synchronises.  A / dX (device, may be NULL slots) receive the per-sample outputs. */
+int tops_fflayer_fwd_grad_host(tops_ctx*, const float* X_host, const float* dA_host, int64_t B, const tops_buf* W, const tops_buf* b,
+                               int act, int n_chunks, tops_buf** A, tops_buf** dX, tops_buf** grads, float* grads_host);
 /* netGrad (FeedForward.hs:178-199) of a genNet-style network (FeedForward.hs:216-235) over a batch:
  *   layers l = 0..n-1 with W[l], b[l], acts[l]; loss on (A_out, Y); per-sample losses summed into loss_sum (rank 0).
  *   Outputs: A_out[B,o], loss_sum[], dX[B,i] (may be NULL to skip), dW[l], db[l]. */

@@ -21,6 +21,7 @@ struct tops_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D staging of the host-buffer entry points, overlapped with compute on `stream`
     cudaStream_t stream = nullptr;
     std::recursive_mutex mu;
     std::string last_error;
@@ -185,7 +186,7 @@ int run_gemm(tops_ctx* ctx, GemmCall c) {
     const double es_in = c.dtype == 1 ? 2.0 : 4.0, es_out = c.io_bf16 ? 2.0 : 4.0;
     ProfScope prof_(ctx, c.tag ? c.tag : "gemm", 2.0 * c.M * c.N * (double)(c.K > 0 ? c.K : 0),
                     es_in * ((double)c.M * c.K + (double)c.N * c.K) + (c.epi == EPI_ATOMIC ? 4.0 : es_out) * (double)c.M * c.N * ((c.out1 ? 1 : 0) + (c.aux0 ? 1 : 0) + 1));
-    if (c.epi == EPI_ATOMIC) {
+    if (c.epi == EPI_ATOMIC && !c.accumulate) {
         CUDA_TRY(ctx, cudaMemsetAsync(c.out0, 0, sizeof(float) * (size_t)c.M * (size_t)c.ld_out0, ctx->stream));
     }
     if (c.K <= 0) {   // empty contraction: result is the epilogue applied to zeros; only plain store/atomic make sense
@@ -234,6 +235,7 @@ extern "C" int tops_init(int device, tops_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return TOPS_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return TOPS_ERR_CUDA; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
@@ -257,6 +259,7 @@ extern "C" int tops_shutdown(tops_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->wd_host) cudaFreeHost(ctx->wd_host);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return TOPS_OK;
@@ -753,7 +756,7 @@ int layer_shapes(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops
 // `db` (optional, epilogues with a dZ output only): column sums of dZ fused into the epilogue; *db_fused reports whether the
 // kernel produced them (the TMA epilogue does; the direct / SIMT paths leave it to col_sums).
 int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, const float* b, int act, int epi,
-             void* A, const void* aux, void* out1, float* loss, float* db = nullptr, int* db_fused = nullptr) {
+             void* A, const void* aux, void* out1, float* loss, float* db = nullptr, int* db_fused = nullptr, bool db_accumulate = false) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.o; g.K = (int)s.i;
     g.A = X; g.lda = s.i; g.major_a = MAJOR_K;
@@ -762,7 +765,7 @@ int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, 
     g.out0 = A; g.ld_out0 = s.o; g.out1 = out1; g.ld_out1 = s.o; g.aux0 = aux; g.ld_aux0 = s.o; g.loss = loss;
     g.io_bf16 = g.dtype;
     if (db && out1 && s.B > 0) {
-        CUDA_TRY(ctx, cudaMemsetAsync(db, 0, sizeof(float) * (size_t)s.o, ctx->stream));
+        if (!db_accumulate) CUDA_TRY(ctx, cudaMemsetAsync(db, 0, sizeof(float) * (size_t)s.o, ctx->stream));
         g.colsum = db; g.colsum_src = 2; g.colsum_fused = db_fused;
     }
     return run_gemm(ctx, g);
@@ -785,13 +788,14 @@ int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, 
     return run_gemm(ctx, g);
 }
 // dW = dZ^T Xin   (split-K over the batch, fp32 atomics into a zeroed output), db = column sums of dZ
-int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, float* dW, float* db, bool db_done = false) {
+int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, float* dW, float* db, bool db_done = false, bool accumulate = false) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.o; g.N = (int)s.i; g.K = (int)s.B;
     g.A = dZ; g.lda = s.o; g.major_a = MAJOR_MN;
     g.B = Xin; g.ldb = s.i; g.major_b = MAJOR_MN;
-    g.epi = EPI_ATOMIC; g.alpha = 1.f; g.out0 = dW; g.ld_out0 = s.i; g.tag = "gemm_dW";
+    g.epi = EPI_ATOMIC; g.alpha = 1.f; g.out0 = dW; g.ld_out0 = s.i; g.tag = "gemm_dW"; g.accumulate = accumulate ? 1 : 0;
     TRY(run_gemm(ctx, g));
+    if (db && !db_done && accumulate) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "accumulating db needs the fused column sums (aligned fp32/bf16 rows)");
     if (db && !db_done) {
         ProfScope prof_(ctx, "col_sums_db", 0.0, (s.dtype == TOPS_BF16 ? 2.0 : 4.0) * (double)s.B * s.o);
         float* ws = nullptr;
@@ -836,6 +840,70 @@ extern "C" int tops_fflayer_fwd_grad(tops_ctx* ctx, const tops_buf* X, const top
                  db ? (float*)(*db)->data : nullptr, &db_fused));
     TRY(dw_db(ctx, s, dZ->data, X->data, (float*)(*dW)->data, db ? (float*)(*db)->data : nullptr, db_fused != 0));
     if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
+    return TOPS_OK;
+}
+
+// Host-buffer entry point (what the reference's `fromList`-batch -> netGrad -> `toList` round trip becomes): X and dA live in
+// HOST memory.  The batch is cut into row chunks; chunk k+1 crosses PCIe on the copy stream while chunk k runs its three
+// GEMMs on the compute stream, dW/db accumulating across chunks (split-K atomics / fused column sums).  PCIe is the bound.
+extern "C" int tops_fflayer_fwd_grad_host(tops_ctx* ctx, const float* X_host, const float* dA_host, int64_t B, const tops_buf* W, const tops_buf* b,
+                                          int act, int n_chunks, tops_buf** A, tops_buf** dX, tops_buf** grads, float* grads_host) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!X_host || !dA_host || !W || !grads || B < 0) return set_err(ctx, TOPS_ERR_INVALID, "fflayer_fwd_grad_host: NULL argument");
+    if (W->rank != 2 || W->dtype != TOPS_F32 || W->tr || (b && (b->rank != 1 || b->dims[0] != W->dims[0] || b->dtype != TOPS_F32)))
+        return set_err(ctx, TOPS_ERR_SHAPE, "fflayer_fwd_grad_host: W[o,i] b[o] fp32 expected");
+    TRY(check_act(ctx, act));
+    const int64_t o = W->dims[0], i = W->dims[1];
+    int64_t dA_[2] = {B, o}, dX_[2] = {B, i}, g_[1] = {o * i + o};
+    Tmp tmp;
+    tops_buf *Xd = nullptr, *dAd = nullptr, *dZ = nullptr, *Ad = nullptr, *dXd = nullptr;
+    TRY(alloc_buf(ctx, TOPS_F32, 2, dX_, &Xd)); tmp.keep(Xd);
+    TRY(alloc_buf(ctx, TOPS_F32, 2, dA_, &dAd)); tmp.keep(dAd);
+    TRY(alloc_buf(ctx, TOPS_F32, 2, dA_, &dZ)); tmp.keep(dZ);
+    if (A) { TRY(prep_out(ctx, A, TOPS_F32, 2, dA_)); Ad = *A; } else { TRY(alloc_buf(ctx, TOPS_F32, 2, dA_, &Ad)); tmp.keep(Ad); }
+    if (dX) { TRY(prep_out(ctx, dX, TOPS_F32, 2, dX_)); dXd = *dX; } else { TRY(alloc_buf(ctx, TOPS_F32, 2, dX_, &dXd)); tmp.keep(dXd); }
+    TRY(prep_out(ctx, grads, TOPS_F32, 1, g_));
+    float* dW = (float*)(*grads)->data; float* db = dW + o * i;
+    CUDA_TRY(ctx, cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)(o * i + o), ctx->stream));
+    if (n_chunks <= 0) n_chunks = 8;
+    if (n_chunks > 64) n_chunks = 64;
+    int64_t rows_per = ((B + n_chunks - 1) / n_chunks + 127) / 128 * 128;   // whole 128-row tiles per chunk
+    if (rows_per <= 0) rows_per = 128;
+    // the allocations above are stream-ordered on the compute stream: the copy stream must not write before they exist
+    cudaEvent_t ready;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaEventRecord(ready, ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
+    std::vector<cudaEvent_t> ev;
+    for (int64_t r0 = 0; r0 < B; r0 += rows_per) {
+        const int64_t n = (B - r0 < rows_per) ? B - r0 : rows_per;
+        cudaMemcpyAsync((float*)Xd->data + r0 * i, X_host + r0 * i, sizeof(float) * (size_t)(n * i), cudaMemcpyHostToDevice, ctx->copy_stream);
+        cudaMemcpyAsync((float*)dAd->data + r0 * o, dA_host + r0 * o, sizeof(float) * (size_t)(n * o), cudaMemcpyHostToDevice, ctx->copy_stream);
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaEventRecord(e, ctx->copy_stream);
+        ev.push_back(e);
+    }
+    int rc = TOPS_OK;
+    int64_t r0 = 0;
+    for (size_t c = 0; c < ev.size() && rc == TOPS_OK; ++c, r0 += rows_per) {
+        const int64_t n = (B - r0 < rows_per) ? B - r0 : rows_per;
+        cudaStreamWaitEvent(ctx->stream, ev[c], 0);
+        LayerShapes s{n, i, o, TOPS_F32};
+        const float* Xc = (const float*)Xd->data + r0 * i; const float* dAc = (const float*)dAd->data + r0 * o;
+        float* Ac = (float*)Ad->data + r0 * o; float* dZc = (float*)dZ->data + r0 * o; float* dXc = (float*)dXd->data + r0 * i;
+        int fused = 0;
+        rc = fwd_gemm(ctx, s, Xc, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, Ac, dAc, dZc, nullptr, db, &fused, true);
+        if (rc == TOPS_OK) rc = dw_db(ctx, s, dZc, Xc, dW, db, fused != 0, true);
+        if (rc == TOPS_OK) rc = dx_gemm(ctx, s, dZc, W->data, dXc, EPI_STORE, ACT_ID, nullptr);
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    cudaEventDestroy(ready);
+    if (rc != TOPS_OK) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    if (grads_host) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(grads_host, dW, sizeof(float) * (size_t)(o * i + o), cudaMemcpyDeviceToHost, ctx->stream));
+        return tops_sync(ctx);
+    }
     return TOPS_OK;
 }
 

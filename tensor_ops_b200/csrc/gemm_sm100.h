@@ -23,6 +23,7 @@ struct GemmCall {
     int split_k;    // 0 = choose automatically (only EPI_ATOMIC may split)
     int block_n;    // 0 = choose automatically, else 128 or 256
     int max_ctas;   // 0 = number of SMs
+    int accumulate; // EPI_ATOMIC only: add into out0 as it is (the caller zeroed it / is accumulating across calls)
     float* colsum;         // optional [N] fp32 accumulator, PRE-ZEROED by the caller: column sums of out0 (colsum_src 1) / out1 (2)
     int colsum_src;        // 0 = none
     int* colsum_fused;     // out: set to 1 if the kernel produced the column sums (TMA epilogue), else 0 (caller reduces separately)

@@ -196,25 +196,34 @@ def fflayer_fwd_grad(X: CuTensor, W: CuTensor, b: CuTensor, dA: CuTensor, act: i
 
 
 def fflayer_fwd_grad_host(ctx: Context, X_host, W: CuTensor, b: CuTensor, dA_host, act: int = L.ACT_LOGISTIC, grads_out=None,
-                          allreduce: Optional[Callable[[], None]] = None, workspace=None):
-    """Host-buffer entry point of the batched fwd+grad: `fromList` the batch (X, dA: C-contiguous fp32 host arrays, pinned
-    for async copies), run `tops_fflayer_fwd_grad` on the device, `toList` the packed parameter gradient [dW‖db] into
-    `grads_out`.  `workspace` = (X_dev, dA_dev, A_dev, dX_dev, packed_dev) re-uses device buffers between steps;
-    `allreduce` (data-parallel runs) is called on the packed gradient before it is read back."""
+                          allreduce: Optional[Callable[[], None]] = None, workspace=None, n_chunks: int = 0):
+    """Host-buffer entry point of the batched fwd+grad (tops_fflayer_fwd_grad_host): `fromList` the batch (X, dA: C-contiguous
+    fp32 host arrays, pinned for full PCIe rate), run the forward + VJP on the device with the host->device copies of row chunk
+    k+1 overlapping the GEMMs of chunk k, and `toList` the packed parameter gradient [dW‖db] into `grads_out`.
+    `workspace` = (A_dev, dX_dev, packed_dev) re-uses device output buffers between steps; `allreduce` (data-parallel runs) is
+    called on the packed device gradient before it is read back."""
     import numpy as np
     B, i = X_host.shape
     o = W.shape[0]
-    if workspace is None:
-        workspace = (ctx.empty((B, i)), ctx.empty((B, o)), ctx.empty((B, o)), ctx.empty((B, i)), ctx.empty((o * i + o,)))
-    Xd, dAd, Ad, dXd, packed = workspace
-    Xd.upload(X_host)
-    dAd.upload(dA_host)
-    fflayer_fwd_grad(Xd, W, b, dAd, act, out=(Ad, dXd, packed.view(0, (o, i)), packed.view(o * i, (o,))))
-    if allreduce is not None:
-        allreduce()
+    if X_host.dtype != np.float32 or dA_host.dtype != np.float32 or not X_host.flags.c_contiguous or not dA_host.flags.c_contiguous:
+        raise ValueError("fflayer_fwd_grad_host: X and dA must be C-contiguous float32 host arrays")
+    if dA_host.shape != (B, o):
+        raise ValueError("fflayer_fwd_grad_host: dA must be [B, o]")
     if grads_out is None:
         grads_out = np.empty(o * i + o, dtype=np.float32)
-    return packed.download_into(grads_out)
+    slots = [L.c_buf(), L.c_buf(), L.c_buf()]
+    if workspace is not None:
+        for j, t in enumerate(workspace):
+            slots[j] = L.c_buf(t.b.value)
+    direct = allreduce is None
+    ctx.check(L.lib.tops_fflayer_fwd_grad_host(ctx.h, X_host.ctypes.data, dA_host.ctypes.data, B, W.b, b.b, act, n_chunks,
+                                               C.byref(slots[0]), C.byref(slots[1]), C.byref(slots[2]),
+                                               grads_out.ctypes.data if direct else None))
+    outs = list(workspace) if workspace is not None else [CuTensor(ctx, s_) for s_ in slots]
+    if not direct:
+        allreduce()
+        outs[2].download_into(grads_out)
+    return grads_out
 
 
 def fflayer_grad(X: CuTensor, W: CuTensor, b: CuTensor, dA: CuTensor, act: int = L.ACT_LOGISTIC, A_saved: Optional[CuTensor] = None):

@@ -398,3 +398,20 @@ def test_config3_mnist_shaped_mlp_full_batch(ctx):
     assert abs(L.unScalar() - ref[1]) <= 1e-5 * abs(ref[1])
     for l in range(3):
         close(dWs[l], ref[3][l], 1e-5, f"dW{l}"); close(dbs[l], ref[4][l], 1e-5, f"db{l}")
+
+
+@pytest.mark.parametrize("B,n_chunks", [(1000, 3), (64, 0), (5000, 8)])
+def test_host_buffer_entry_point_pipelined(ctx, B, n_chunks):
+    """tops_fflayer_fwd_grad_host: host X/dA in, chunked H2D overlapped with compute, dW/db accumulated across chunks."""
+    ctx.set_precision(tb.PREC_TF32X3)
+    rng = np.random.default_rng(77 + B)
+    i, o = 96, 72
+    X = rng.uniform(-1, 1, (B, i)).astype(np.float32); dA = rng.normal(size=(B, o)).astype(np.float32)
+    W = rng.normal(0, 0.5, (o, i)).astype(np.float32); b = rng.normal(0, 0.5, o).astype(np.float32)
+    ref = O.fflayer_logistic_dense(X.astype(np.float64), W.astype(np.float64), b.astype(np.float64), dA.astype(np.float64))
+    A = ctx.empty((B, o)); dX = ctx.empty((B, i)); packed = ctx.empty((o * i + o,))
+    g = nn.fflayer_fwd_grad_host(ctx, X, ctx.from_numpy(W), ctx.from_numpy(b), dA, workspace=(A, dX, packed), n_chunks=n_chunks)
+    close(A, ref[0], 1e-5, "A host path"); close(dX, ref[1], 1e-5, "dX host path")
+    close(g[:o * i].reshape(o, i), ref[2], 1e-5, "dW host path"); close(g[o * i:], ref[3], 1e-5, "db host path")
+    # the device copy of the packed gradient is what a data-parallel run all-reduces
+    assert np.array_equal(packed.numpy(), g)
