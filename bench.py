@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.004)
 
     def stop(self):
         self._stop_evt.set()

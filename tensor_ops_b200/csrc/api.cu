@@ -208,6 +208,14 @@ int run_gemm(tops_ctx* ctx, GemmCall c) {
     return TOPS_OK;
 }
 
+// A plain-store GEMM with few output tiles and a long contraction (e.g. the dy VJP of a rank-3 gmul: 64x64 outputs, K = 4096)
+// would run on a handful of SMs: switch it to split-K partials accumulated with fp32 reds (run_gemm zeroes the output).
+void split_k_if_skinny(tops_ctx* ctx, GemmCall& g) {
+    if (g.epi != EPI_STORE || g.aux0 != nullptr || g.io_bf16) return;
+    const long long tiles = ((g.M + 127) / 128) * (long long)((g.N + 255) / 256);
+    if (tiles * 4 <= ctx->num_sms && g.K >= 1024) { g.epi = EPI_ATOMIC; g.split_k = 0; }
+}
+
 // describe a rank-2 fp32/bf16 matrix (possibly a transposed view) as a GEMM operand whose reduction runs over `k_axis`
 // of its LOGICAL shape.  Returns pointer/ld/major for the engine's  sum_k P(mn, k)  convention.
 void as_operand(const tops_buf* m, int k_axis, const void** ptr, long long* ld, int* major) {
@@ -476,6 +484,7 @@ extern "C" int tops_gemm(tops_ctx* ctx, double alpha, const tops_buf* a, const t
     g.epi = EPI_STORE; g.alpha = (float)alpha; g.beta = (float)beta; g.tag = "gemm";
     g.out0 = (*out)->data; g.ld_out0 = d[1];
     if (cs) { g.aux0 = cs->data; g.ld_aux0 = d[1]; }
+    else split_k_if_skinny(ctx, g);
     return run_gemm(ctx, g);
 }
 extern "C" int tops_index(tops_ctx* ctx, const tops_buf* x, const int64_t* idx, double* value) {
@@ -670,6 +679,7 @@ extern "C" int tops_gmul(tops_ctx* ctx, int lM, int lO, int lN, const tops_buf* 
     g.A = xd; g.lda = xs->tr ? Mx : O; g.major_a = xs->tr ? MAJOR_MN : MAJOR_K;
     g.B = yd; g.ldb = yp->tr ? O : N; g.major_b = yp->tr ? MAJOR_K : MAJOR_MN;
     g.epi = EPI_STORE; g.alpha = 1.f; g.beta = 0.f; g.out0 = o; g.ld_out0 = N; g.tag = "gmul";
+    split_k_if_skinny(ctx, g);
     return run_gemm(ctx, g);
 }
 

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Measures the other BASELINE.json configs on one GPU (not the driver's bench line; numbers go into DESIGN.md / profiles/):
+   config 3: MLP 784->512->256->10, logistic/logistic/softmax + crossEntropy, batch 32768, fp32 (netGrad over the batch)
+   config 4: ffLayer 4096->4096, bf16 storage / fp32 accumulate, batch 262144 (per GPU share at 1 GPU), fwd+grad
+   config 5: rank-3 contraction  x[64,64,64] . y[64,64] -> [64,64,64] -> sumRows -> [64,64], fwd + VJP
+   usage: python tools/bench_configs.py [3] [4] [5]"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import tensor_ops_b200 as tb
+from tensor_ops_b200 import nn, _lib as L, top as TO
+from tensor_ops_b200.tensor import CuTensor
+
+ctx = tb.Context(0)
+PEAK_BF16 = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["bf16_tflops"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 1590.0
+PEAK_HBM = 6546.2
+
+
+def timeit(fn, steps=10, warm=3):
+    for _ in range(warm): fn()
+    ctx.sync(); ctx.profile(True)
+    t0 = time.perf_counter()
+    for _ in range(steps): fn()
+    prof = ctx.profile_summary(); ctx.profile(False)     # synchronises
+    wall = (time.perf_counter() - t0) / steps * 1e3
+    return wall, {k: v["ms"] / v["launches"] * (v["launches"] / steps) for k, v in prof.items()}
+
+
+which = set(sys.argv[1:]) or {"3", "4", "5"}
+if "3" in which:
+    B, dims = 32768, [784, 512, 256, 10]
+    Ws = [ctx.rand_normal((dims[l + 1], dims[l]), 0, 0.5 / np.sqrt(dims[l]) * 2, seed=10 + l) for l in range(3)]
+    bs = [ctx.rand_normal((dims[l + 1],), 0, 0.5, seed=20 + l) for l in range(3)]
+    X = ctx.rand_uniform((B, 784), 0, 1, seed=1)
+    Yh = np.zeros((B, 10), np.float32); Yh[np.arange(B), np.random.default_rng(0).integers(0, 10, B)] = 1
+    Y = ctx.from_numpy(Yh)
+    acts = [L.ACT_LOGISTIC, L.ACT_LOGISTIC, L.ACT_SOFTMAX]
+    for prec, name in ((tb.PREC_TF32X3, "tf32x3"), (tb.PREC_TF32, "tf32")):
+        ctx.set_precision(prec)
+        ms, per = timeit(lambda: nn.mlp_fwd_grad(Ws, bs, acts, L.LOSS_CROSS_ENTROPY, X, Y))
+        flop = 6.0 * B * (784 * 512 + 512 * 256 + 256 * 10)
+        print(json.dumps({"config": 3, "precision": name, "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "tflops_algorithmic": flop / ms / 1e9,
+                          "frac_of_tf32_peak": flop / ms / 1e9 / (PEAK_BF16 / 2), "per_step_kernel_ms": per}), flush=True)
+if "4" in which:
+    B, n = 262144, 4096
+    Xf = ctx.rand_uniform((B, n), -1, 1, seed=1); X = Xf.cast(L.BF16); del Xf
+    dAf = ctx.rand_normal((B, n), 0, 1, seed=2); dA = dAf.cast(L.BF16); del dAf
+    Wf = ctx.rand_normal((n, n), 0, 0.5 / 64 * 2, seed=3); W = Wf.cast(L.BF16); del Wf
+    b = ctx.rand_normal((n,), 0, 0.5, seed=4)
+    outs = (ctx.empty((B, n), L.BF16), ctx.empty((B, n), L.BF16), ctx.empty((n, n)), ctx.empty((n,)))
+    ms, per = timeit(lambda: nn.fflayer_fwd_grad(X, W, b, dA, out=outs), steps=5)
+    flop = 6.0 * B * n * n
+    print(json.dumps({"config": 4, "precision": "bf16 storage, fp32 accumulate", "ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+                      "tflops_algorithmic": flop / ms / 1e9, "frac_of_bf16_peak": flop / ms / 1e9 / PEAK_BF16, "per_step_kernel_ms": per}), flush=True)
+if "5" in which:
+    rng = np.random.default_rng(5)
+    x = ctx.from_numpy(rng.normal(size=(64, 64, 64))); y = ctx.from_numpy(rng.normal(size=(64, 64))); d = ctx.from_numpy(rng.normal(size=(64, 64)))
+    op = TO.compose(TO.sumRows(), TO.inner(2, 1))      # inner (LS (LS LZ)) (LS LZ) >>> sumRows   (SURVEY §8-d note on config 5)
+    for prec, name in ((tb.PREC_TF32X3, "tf32x3"), (tb.PREC_FP32_SIMT, "simt")):
+        ctx.set_precision(prec)
+        def step():
+            TO.runTOp(op, [x, y]); TO.gradTOp_(op, [x, y], [d])
+        n0 = ctx.launch_count(); step(); launches = ctx.launch_count() - n0
+        ms, per = timeit(step, steps=20)
+        bytes_alg = 3.1 * 2 ** 20
+        print(json.dumps({"config": 5, "precision": name, "ms_per_step": ms, "kernel_launches_per_step": launches, "algorithmic_GB_s": bytes_alg / ms / 1e6,
+                          "frac_of_hbm_peak": bytes_alg / ms / 1e6 / PEAK_HBM, "note": "launch-latency dominated: 3.1 MiB of traffic per step", "per_step_kernel_ms": per}), flush=True)
