@@ -99,51 +99,77 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
-def cpu_reference_rate(seconds_target, i, o, dtype_name="float32", max_samples=4096):
-    """The oracle's per-sample restatement of the reference's hmatrix op sequence (gemv, axpy, cmap logistic, recomputed
-    forward, ger, gemv (tr W)) on a bounded sample of the workload; returns (samples/s, n_samples, seconds)."""
+def cpu_step_all_cores(O, X, W, b, dA, threads):
+    """The reference's per-sample op sequence (oracle.cpu_fflayer_step_reference: gemv, axpy, cmap logistic, recomputed forward,
+    ger, gemv (tr W)) over a batch.  The reference itself is single-threaded (no par/forkIO anywhere); to give the CPU arm every
+    host core, samples are split across `threads` Python threads (NumPy/OpenBLAS release the GIL; BLAS pinned to 1 thread per
+    call to avoid oversubscription) and the per-thread parameter gradients are summed."""
+    if threads <= 1:
+        return O.cpu_fflayer_step_reference(X, W, b, dA)
+    from concurrent.futures import ThreadPoolExecutor
+    import numpy as np
+    bounds = np.linspace(0, X.shape[0], threads + 1).astype(int)
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(lambda k: O.cpu_fflayer_step_reference(X[bounds[k]:bounds[k + 1]], W, b, dA[bounds[k]:bounds[k + 1]]), range(threads)))
+    return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), sum(p[2] for p in parts), sum(p[3] for p in parts))
+
+
+def _blas_single_thread():
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def cpu_reference_rate(seconds_target, i, o, dtype_name="float32", max_samples=16384):
+    """Times the CPU port on a bounded sample of the workload with all host cores; returns (samples/s, n_samples, seconds, threads)."""
     import numpy as np
     from oracle import tensor_ops_oracle as O
+    threads = os.cpu_count() or 1
     dt = np.dtype(dtype_name)
     rng = np.random.default_rng(0)
     W = rng.normal(0, 0.5, (o, i)).astype(dt); b = rng.normal(0, 0.5, o).astype(dt)
-    probe = 16
-    X = rng.uniform(-1, 1, (probe, i)).astype(dt); dA = rng.standard_normal((probe, o)).astype(dt)
-    O.cpu_fflayer_step_reference(X, W, b, dA)
-    t0 = time.perf_counter(); O.cpu_fflayer_step_reference(X, W, b, dA); per = (time.perf_counter() - t0) / probe
-    n = int(max(32, min(max_samples, seconds_target / max(per, 1e-9))))
-    X = rng.uniform(-1, 1, (n, i)).astype(dt); dA = rng.standard_normal((n, o)).astype(dt)
-    t0 = time.perf_counter(); O.cpu_fflayer_step_reference(X, W, b, dA); dtm = time.perf_counter() - t0
-    return n / dtm, n, dtm
+    with _blas_single_thread():
+        probe = 16 * threads
+        X = rng.uniform(-1, 1, (probe, i)).astype(dt); dA = rng.standard_normal((probe, o)).astype(dt)
+        cpu_step_all_cores(O, X, W, b, dA, threads)
+        t0 = time.perf_counter(); cpu_step_all_cores(O, X, W, b, dA, threads); per = (time.perf_counter() - t0) / probe
+        n = int(max(32, min(max_samples, seconds_target / max(per, 1e-9))))
+        X = rng.uniform(-1, 1, (n, i)).astype(dt); dA = rng.standard_normal((n, o)).astype(dt)
+        t0 = time.perf_counter(); cpu_step_all_cores(O, X, W, b, dA, threads); dtm = time.perf_counter() - t0
+    return n / dtm, n, dtm, threads
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Haskell (no GHC in this
-    image, no C sources to compile), so this executes the oracle port on all host threads the BLAS will use."""
+    image, no C sources to compile), so this executes the oracle port of its hmatrix op sequence on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import numpy as np
     from oracle import tensor_ops_oracle as O
     i, o = CFG["i"], CFG["o"]
+    threads = os.cpu_count() or 1
     rng = np.random.default_rng(0)
     W = rng.normal(0, 0.5, (o, i)).astype(np.float32); b = rng.normal(0, 0.5, o).astype(np.float32)
-    n = 256   # samples per step: a bounded sample of the 65536-row batch
+    n = 64 * threads   # samples per step: a bounded sample of the 65536-row batch
     X = rng.uniform(-1, 1, (n, i)).astype(np.float32); dA = rng.standard_normal((n, o)).astype(np.float32)
-    for _ in range(args.warmup):
-        O.cpu_fflayer_step_reference(X[:32], W, b, dA[:32])
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.cpu_fflayer_step_reference(X, W, b, dA)
-    dt = time.perf_counter() - t0
+    with _blas_single_thread():
+        for _ in range(args.warmup):
+            cpu_step_all_cores(O, X[:4 * threads], W, b, dA[:4 * threads], threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_step_all_cores(O, X, W, b, dA, threads)
+        dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    cores = os.cpu_count()
     line = {"impl": "reference", "metric": "ffLayer fwd+grad samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": f"{n} samples per step of the 65536-sample batch"},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} samples/step x {args.steps} steps, per-sample hmatrix op sequence (oracle.cpu_fflayer_step_reference), NumPy/OpenBLAS fp32, {cores} threads available"},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} samples/step x {args.steps} steps, per-sample hmatrix op sequence (oracle.cpu_fflayer_step_reference), NumPy/OpenBLAS fp32, samples split over {threads} threads"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -340,9 +366,9 @@ def main():
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
-        v, n, secs = cpu_reference_rate(12.0, i, o)
-        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{n} samples of the batch in {secs:.1f} s: per-sample hmatrix op sequence restated in NumPy/OpenBLAS fp32 (oracle.cpu_fflayer_step_reference)"}
+        v, n, secs, threads = cpu_reference_rate(12.0, i, o)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                "sample": f"{n} samples of the batch in {secs:.1f} s: per-sample hmatrix op sequence restated in NumPy/OpenBLAS fp32 (oracle.cpu_fflayer_step_reference), samples split over {threads} threads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -522,13 +522,19 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     uint32_t first = 1;
                     for (int kb = kc; kb < kce; ++kb) {
-                        ptx::mbar_wait(PASSES == 3 ? &ready_bar[s] : &full_bar[s], ph, wd, 0x300 + s);
+                        ptx::mbar_wait(&full_bar[s], ph, wd, 0x300 + s);
                         ptx::tcgen05_fence_after();
                         const uint32_t sa = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
                         const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
                         for (int pass = 0; pass < PASSES; ++pass) {
                             // pass 0: A_hi*B_hi   pass 1: A_lo*B_hi   pass 2: A_hi*B_lo
+                            // pass 0 needs only the raw tiles, so it is issued as soon as the TMA data lands and runs on the
+                            // tensor pipe while the splitter warps are still producing the lo tiles for passes 1 and 2
+                            if (PASSES == 3 && pass == 1) {
+                                ptx::mbar_wait(&ready_bar[s], ph, wd, 0x340 + s);
+                                ptx::tcgen05_fence_after();
+                            }
                             const uint32_t pa = sa + (pass == 1 ? Cfg::RAW_BYTES : 0);
                             const uint32_t pb = sb + (pass == 2 ? Cfg::RAW_BYTES : 0);
 #pragma unroll
