@@ -48,43 +48,58 @@ bool make_map(CUtensorMap* m, int dtype, const void* ptr, long long inner, long 
     return r == CUDA_SUCCESS;
 }
 
-template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
 cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-    using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES>;
-    auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES>;
+    using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
+    auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES, CG>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], p);
-    return cudaGetLastError();
+    if constexpr (CG == 1) {
+        kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], p);
+        return cudaGetLastError();
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::NUM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], p);
+    }
+}
+
+template <typename T, int MA, int MB, int CG>
+cudaError_t launch_cg(int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+    // stage bytes: 1-pass (128 + bn/CG) * 128, 3-pass twice that; stage counts fill the 227 KiB left after the epilogue staging
+    if constexpr (sizeof(T) == 4) {
+        if (passes == 3) {
+            if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 4 : 3, 3, CG>(tm, p, grid, st);
+            return launch_one<T, MA, MB, 256, CG == 2 ? 3 : 2, 3, CG>(tm, p, grid, st);
+        }
+        // fp32 1-pass: one stage fewer than fits, so that each epilogue warp gets separate aux and output staging blocks
+        if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 6 : 5, 1, CG>(tm, p, grid, st);
+        return launch_one<T, MA, MB, 256, CG == 2 ? 5 : 3, 1, CG>(tm, p, grid, st);
+    }
+    if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 8 : 6, 1, CG>(tm, p, grid, st);
+    return launch_one<T, MA, MB, 256, CG == 2 ? 6 : 4, 1, CG>(tm, p, grid, st);
 }
 
 template <typename T, int MA, int MB>
-cudaError_t launch_major(int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-    if constexpr (sizeof(T) == 4) {
-        if (passes == 3) {
-            if (bn == 128) return launch_one<T, MA, MB, 128, 3, 3>(tm, p, grid, st);
-            return launch_one<T, MA, MB, 256, 2, 3>(tm, p, grid, st);
-        }
-    }
-    // fp32 1-pass: one stage fewer than fits, so that each epilogue warp gets separate aux and output staging blocks
-    if constexpr (sizeof(T) == 4) {
-        if (bn == 128) return launch_one<T, MA, MB, 128, 5, 1>(tm, p, grid, st);
-        return launch_one<T, MA, MB, 256, 3, 1>(tm, p, grid, st);
-    }
-    if (bn == 128) return launch_one<T, MA, MB, 128, 6, 1>(tm, p, grid, st);
-    return launch_one<T, MA, MB, 256, 4, 1>(tm, p, grid, st);
+cudaError_t launch_major(int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+    if (cg == 2) return launch_cg<T, MA, MB, 2>(bn, passes, tm, p, grid, st);
+    return launch_cg<T, MA, MB, 1>(bn, passes, tm, p, grid, st);
 }
 
 template <typename T>
-cudaError_t launch_dtype(int ma, int mb, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-    if (ma == MAJOR_K && mb == MAJOR_K) return launch_major<T, MAJOR_K, MAJOR_K>(bn, passes, tm, p, grid, st);
-    if (ma == MAJOR_K && mb == MAJOR_MN) return launch_major<T, MAJOR_K, MAJOR_MN>(bn, passes, tm, p, grid, st);
-    if (ma == MAJOR_MN && mb == MAJOR_K) return launch_major<T, MAJOR_MN, MAJOR_K>(bn, passes, tm, p, grid, st);
-    return launch_major<T, MAJOR_MN, MAJOR_MN>(bn, passes, tm, p, grid, st);
+cudaError_t launch_dtype(int cg, int ma, int mb, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+    if (ma == MAJOR_K && mb == MAJOR_K) return launch_major<T, MAJOR_K, MAJOR_K>(cg, bn, passes, tm, p, grid, st);
+    if (ma == MAJOR_K && mb == MAJOR_MN) return launch_major<T, MAJOR_K, MAJOR_MN>(cg, bn, passes, tm, p, grid, st);
+    if (ma == MAJOR_MN && mb == MAJOR_K) return launch_major<T, MAJOR_MN, MAJOR_K>(cg, bn, passes, tm, p, grid, st);
+    return launch_major<T, MAJOR_MN, MAJOR_MN>(cg, bn, passes, tm, p, grid, st);
 }
 
 }  // namespace
@@ -102,6 +117,11 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     if (bn == 0) bn = (c.N <= 128) ? 128 : 256;
     if (bn != 128 && bn != 256) return fail(-1, "gemm: block_n must be 128 or 256");
 
+    // CTA pairs (cta_group::2): a 2-CTA cluster computes a 256-row tile, each CTA staging its 128 rows of A and half of the B
+    // tile — per-SM shared-memory traffic per MMA drops from 12 KiB to 8 KiB, which is what bounds the 1-CTA kernels.
+    int cg = c.cta_group;
+    if (cg == 0) cg = (c.M > 128) ? 2 : 1;
+    if (cg != 1 && cg != 2) return fail(-1, "gemm: cta_group must be 0 (auto), 1 or 2");
     CUtensorMap tm[3];   // A, B, aux0
     CUtensorMap &ta = tm[0], &tb = tm[1];
     memset(tm, 0, sizeof tm);
@@ -109,7 +129,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     if (c.major_a == MAJOR_K) ok = make_map(&ta, c.dtype, c.A, c.K, c.M, c.lda, kb_elems, 128, SWZ_128);
     else ok = make_map(&ta, c.dtype, c.A, c.M, c.K, c.lda, kb_elems, kb_elems, c.dtype == 0 ? SWZ_128_ATOM32 : SWZ_128);
     if (!ok) return fail(-1, "gemm: operand A not expressible as a TMA tensor map (alignment/stride)");
-    if (c.major_b == MAJOR_K) ok = make_map(&tb, c.dtype, c.B, c.K, c.N, c.ldb, kb_elems, bn, SWZ_128);
+    if (c.major_b == MAJOR_K) ok = make_map(&tb, c.dtype, c.B, c.K, c.N, c.ldb, kb_elems, bn / cg, SWZ_128);
     else ok = make_map(&tb, c.dtype, c.B, c.N, c.K, c.ldb, kb_elems, kb_elems, c.dtype == 0 ? SWZ_128_ATOM32 : SWZ_128);
     if (!ok) return fail(-1, "gemm: operand B not expressible as a TMA tensor map (alignment/stride)");
     // Staged epilogue: outputs are transposed through shared memory and written with coalesced 16-byte stores, the aux operand
@@ -126,11 +146,11 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     }
     GemmParams p{};
     p.M = c.M; p.N = c.N; p.K = c.K;
-    p.num_m_tiles = (c.M + 127) / 128;
+    p.num_m_tiles = (c.M + 128 * cg - 1) / (128 * cg);
     p.num_n_tiles = (c.N + bn - 1) / bn;
     p.num_k_blocks = (c.K + kb_elems - 1) / kb_elems;
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int ctas = c.max_ctas > 0 ? c.max_ctas : num_sms;
+    const int ctas = (c.max_ctas > 0 ? c.max_ctas : num_sms) / cg;   // CTA groups that can be resident
     int split = c.split_k;
     if (c.epi != EPI_ATOMIC) split = 1;
     else if (split <= 0) {
@@ -169,10 +189,10 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     if (c.epi == EPI_ATOMIC) p.vec_ok = (reinterpret_cast<uintptr_t>(c.out0) & 15) == 0 && (c.ld_out0 % 4) == 0;
 
     const int total = tiles * p.split_k;
-    const int grid = total < ctas ? total : ctas;
+    const int grid = (total < ctas ? total : ctas) * cg;
     cudaError_t e;
-    if (c.dtype == 1) e = launch_dtype<__nv_bfloat16>(c.major_a, c.major_b, bn, 1, tm, p, grid, stream);
-    else e = launch_dtype<float>(c.major_a, c.major_b, bn, c.passes == 3 ? 3 : 1, tm, p, grid, stream);
+    if (c.dtype == 1) e = launch_dtype<__nv_bfloat16>(cg, c.major_a, c.major_b, bn, 1, tm, p, grid, stream);
+    else e = launch_dtype<float>(cg, c.major_a, c.major_b, bn, c.passes == 3 ? 3 : 1, tm, p, grid, stream);
     if (e != cudaSuccess) {
         if (err && errlen) snprintf(err, errlen, "gemm launch: %s", cudaGetErrorString(e));
         return (int)e;

@@ -65,14 +65,15 @@ struct GemmParams {
     unsigned int* watchdog;   // mapped host memory, 2 words
 };
 
-template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
 struct GemmCfg {
     static constexpr int BM = 128;
     static constexpr int KB_ELEMS = 128 / (int)sizeof(T);   // K elements per stage (one 128B swizzle row)
     static constexpr int UMMA_K = 32 / (int)sizeof(T);      // K elements per tcgen05.mma
     static constexpr int KSTEPS = KB_ELEMS / UMMA_K;        // = 4
     static constexpr int A_BYTES = BM * 128;
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int B_BYTES = (BN / CG) * 128;   // a CTA pair (CG = 2) splits the B tile: each CTA stages N/2 rows
+    static_assert(CG == 1 || CG == 2, "CTA group size");
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGE_BYTES = RAW_BYTES * (PASSES == 3 ? 2 : 1);
     static constexpr int NUM_THREADS = PASSES == 3 ? 512 : 384;
@@ -407,11 +408,11 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, const CUtensorMap
     }
 }
 
-template <typename T, int MA, int MB, int BN, int STAGES, int PASSES>
-__global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES>::NUM_THREADS), 1)
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
+__global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>::NUM_THREADS), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAux,
                  const GemmParams p) {
-    using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES>;
+    using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
     constexpr bool kBF16 = sizeof(T) == 2;
     constexpr bool kChunked = PASSES == 3;   // TMEM holds one chunk; the running sum lives in epilogue registers
     constexpr int BM = Cfg::BM;
@@ -433,6 +434,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     volatile unsigned int* wd = p.watchdog;
+    // CTA pair (CG = 2): the two CTAs of a cluster own rows [0,128) and [128,256) of a 256-row tile and half of the B tile each;
+    // the leader (rank 0) issues tcgen05.mma.cta_group::2 for both.  All cross-CTA signalling goes through mbarriers of the leader
+    // (remote arrives) or through multicast commits (same barrier offset in both CTAs).
+    const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int wid0 = blockIdx.x / CG, wstride = gridDim.x / CG;   // work items are distributed over CTA groups
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -443,21 +450,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
-            ptx::mbar_init(&ready_bar[s], 128);
+            // ready: CG = 1: the 128 splitter threads (3-pass).  CG = 2: splitter threads of both CTAs (3-pass) or the two
+            // relay threads that forward "my TMA data has landed" to the leader (1-pass)
+            ptx::mbar_init(&ready_bar[s], CG == 1 ? 128 : (PASSES == 3 ? 256 : 2));
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
-            ptx::mbar_init(&tmem_empty[a], Cfg::EPI_THREADS);
+            ptx::mbar_init(&tmem_empty[a], CG * Cfg::EPI_WARPS);   // one elected lane per epilogue warp (of both CTAs)
         }
         for (int e = 0; e < Cfg::EPI_WARPS; ++e) ptx::mbar_init(&epi_bar[e], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if constexpr (CG == 2) { ptx::tmem_alloc_2cta(tmem_ptr, Cfg::TMEM_COLS); ptx::tmem_relinquish_2cta(); }
+        else { ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -471,13 +481,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (warp == 0 && lane == 0) {
             // ===================================================== TMA producer
             int s = 0; uint32_t ph = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int w = wid0; w < total_work; w += wstride) {
                 const int tile = w % num_tiles, split = w / num_tiles;
-                const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+                const int m0 = (tile / p.num_n_tiles) * (BM * CG) + (int)cta_rank * BM;            // this CTA's 128 rows
+                const int n0 = (tile % p.num_n_tiles) * BN + (int)cta_rank * (BN / CG);            // this CTA's share of the B tile
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(&empty_bar[s], ph ^ 1, wd, 0x100 + s);
+                    if constexpr (CG == 2) ptx::mbar_wait_cluster(&empty_bar[s], ph ^ 1, wd, 0x100 + s);
+                    else ptx::mbar_wait(&empty_bar[s], ph ^ 1, wd, 0x100 + s);
                     ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::RAW_BYTES);
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
@@ -492,15 +504,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         ptx::tma_load_2d(sb, &tmB, &full_bar[s], kb * KB, n0);
                     } else {
 #pragma unroll
-                        for (int r = 0; r < BN / KB; ++r)
+                        for (int r = 0; r < (BN / CG) / KB; ++r)
                             ptx::tma_load_2d(sb + r * (KB * 128), &tmB, &full_bar[s], n0 + r * KB, kb * KB);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ===================================================== MMA issuer
-            constexpr uint32_t idesc = ptx::make_idesc(kBF16 ? 1u : 2u, MA == MAJOR_MN, MB == MAJOR_MN, BM, BN);
+        } else if (warp == 1 && lane == 0 && leader) {
+            // ===================================================== MMA issuer (CG = 2: the leader CTA issues for the pair)
+            constexpr uint32_t idesc = ptx::make_idesc(kBF16 ? 1u : 2u, MA == MAJOR_MN, MB == MAJOR_MN, BM * CG, BN);
             // byte advance of the descriptor start address per UMMA_K step, and the LBO/SBO of each layout
             constexpr uint32_t a_step = (MA == MAJOR_K) ? 32u : (uint32_t)Cfg::UMMA_K * 128u;
             constexpr uint32_t b_step = (MB == MAJOR_K) ? 32u : (uint32_t)Cfg::UMMA_K * 128u;
@@ -510,19 +522,22 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t a_lt = (MA == MAJOR_MN && !kBF16) ? 1u : 2u, b_lt = (MB == MAJOR_MN && !kBF16) ? 1u : 2u;
             constexpr uint32_t a_sbo = a_lt == 1u ? 512u : 1024u, b_sbo = b_lt == 1u ? 512u : 1024u;
             int s = 0; uint32_t ph = 0; int it = 0;   // `it` counts accumulation units: work items (1-pass) or chunks (3-pass)
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int w = wid0; w < total_work; w += wstride) {
                 const int split = w / num_tiles;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
                 for (int kc = kb0; kc < kb1; kc += chunk_kb, ++it) {
                     const int kce = min(kc + chunk_kb, kb1);
                     const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-                    ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, wd, 0x200 + acc);
+                    if constexpr (CG == 2) ptx::mbar_wait_cluster(&tmem_empty[acc], acc_ph ^ 1, wd, 0x200 + acc);
+                    else ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, wd, 0x200 + acc);
                     ptx::tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     uint32_t first = 1;
                     for (int kb = kc; kb < kce; ++kb) {
-                        ptx::mbar_wait(&full_bar[s], ph, wd, 0x300 + s);
+                        // CG = 2: `ready` collects both CTAs (relay threads / splitter threads); the leader's own `full` is implied
+                        if constexpr (CG == 2) ptx::mbar_wait_cluster(&ready_bar[s], ph, wd, 0x300 + s);
+                        else ptx::mbar_wait(&full_bar[s], ph, wd, 0x300 + s);
                         ptx::tcgen05_fence_after();
                         const uint32_t sa = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
                         const uint32_t sb = sa + Cfg::A_BYTES;
@@ -531,7 +546,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             // pass 0: A_hi*B_hi   pass 1: A_lo*B_hi   pass 2: A_hi*B_lo
                             // pass 0 needs only the raw tiles, so it is issued as soon as the TMA data lands and runs on the
                             // tensor pipe while the splitter warps are still producing the lo tiles for passes 1 and 2
-                            if (PASSES == 3 && pass == 1) {
+                            if (PASSES == 3 && pass == 1 && CG == 1) {
                                 ptx::mbar_wait(&ready_bar[s], ph, wd, 0x340 + s);
                                 ptx::tcgen05_fence_after();
                             }
@@ -541,15 +556,36 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int j = 0; j < Cfg::KSTEPS; ++j) {
                                 const uint64_t ad = ptx::make_smem_desc_sw128(pa + j * a_step, a_lbo, a_sbo, a_lt);
                                 const uint64_t bd = ptx::make_smem_desc_sw128(pb + j * b_step, b_lbo, b_sbo, b_lt);
-                                if constexpr (kBF16) ptx::umma_f16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-                                else ptx::umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                if constexpr (CG == 2) {
+                                    if constexpr (kBF16) ptx::umma_f16_2cta(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                    else ptx::umma_tf32_2cta(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                } else {
+                                    if constexpr (kBF16) ptx::umma_f16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                    else ptx::umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                }
                                 first = 0;
                             }
                         }
-                        ptx::umma_commit(&empty_bar[s]);
+                        if constexpr (CG == 2) ptx::umma_commit_2cta(&empty_bar[s], 0x3);   // frees the stage in both CTAs
+                        else ptx::umma_commit(&empty_bar[s]);
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
-                    ptx::umma_commit(&tmem_full[acc]);
+                    if constexpr (CG == 2) ptx::umma_commit_2cta(&tmem_full[acc], 0x3);
+                    else ptx::umma_commit(&tmem_full[acc]);
+                }
+            }
+        } else if (CG == 2 && PASSES == 1 && warp == 3 && lane == 0) {
+            // ===================================================== relay (CTA pair, 1-pass): forward "my stage has landed" to the leader
+            const uint32_t ready0 = ptx::mapa(ptx::smem_u32(&ready_bar[0]), 0);
+            int s = 0; uint32_t ph = 0;
+            for (int w = wid0; w < total_work; w += wstride) {
+                const int split = w / num_tiles;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    ptx::mbar_wait(&full_bar[s], ph, wd, 0x700 + s);
+                    ptx::mbar_arrive_cluster(ready0 + s * 8);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -566,11 +602,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ew.aux_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
         ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * Cfg::EPI_BLOCK_BYTES;
         ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false;
+        const uint32_t tmem_empty0 = CG == 2 ? ptx::mapa(ptx::smem_u32(&tmem_empty[0]), 0) : 0u;   // the leader's accumulator-free barriers
         int it = 0;
         float loss_acc = 0.f;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        for (int w = wid0; w < total_work; w += wstride, ++it) {
             const int tile = w % num_tiles;
-            const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN + half * HC;
+            const int m0 = (tile / p.num_n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (tile % p.num_n_tiles) * BN + half * HC;
             const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
@@ -578,7 +615,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int nblk = (row0 < p.M && ncols > 0) ? (ncols + W - 1) / W : 0;   // W-column blocks this warp owns in this tile
             if (tma && nblk > 0 && epi_has_aux(p))                            // the first aux block does not depend on the accumulators
                 epi_issue_aux<T, W>(&tmAux, ew, lane, row0, n0);
-            ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
+            if constexpr (CG == 2) ptx::mbar_wait_cluster(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
+            else ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
             ptx::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + half * HC + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
@@ -594,7 +632,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 else if (row < p.M) epi_direct<W>(p, row, col, vec, v, loss_acc);
             }
             ptx::tcgen05_fence_before();
-            ptx::mbar_arrive(&tmem_empty[acc]);
+            __syncwarp();
+            if (lane == 0) { if constexpr (CG == 2) ptx::mbar_arrive_cluster(tmem_empty0 + acc * 8); else ptx::mbar_arrive(&tmem_empty[acc]); }
         }
         if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {
 #pragma unroll
@@ -613,11 +652,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ew.aux_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
         ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * Cfg::EPI_BLOCK_BYTES;
         ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false;
+        const uint32_t tmem_empty0 = CG == 2 ? ptx::mapa(ptx::smem_u32(&tmem_empty[0]), 0) : 0u;   // the leader's accumulator-free barriers
         int it = 0;
         float loss_acc = 0.f;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int w = wid0; w < total_work; w += wstride) {
             const int tile = w % num_tiles, split = w / num_tiles;
-            const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+            const int m0 = (tile / p.num_n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (tile % p.num_n_tiles) * BN;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
             if (tma && epi_has_aux(p) && m0 + q * 32 < p.M && n0 + half * HC < p.N)   // first aux block: requested before the K loop
@@ -627,7 +667,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int e = 0; e < HC; ++e) sum[e] = 0.f;
             for (int kc = kb0; kc < kb1; kc += chunk_kb, ++it) {
                 const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-                ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
+                if constexpr (CG == 2) ptx::mbar_wait_cluster(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
+                else ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
                 ptx::tcgen05_fence_after();
                 const uint32_t t_row = tmem_base + acc * BN + half * HC + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
@@ -639,7 +680,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int e = 0; e < 16; ++e) sum[c * 16 + e] += __uint_as_float(raw[e]);   // fp32 add, round to nearest
                 }
                 ptx::tcgen05_fence_before();
-                ptx::mbar_arrive(&tmem_empty[acc]);
+                __syncwarp();
+                if (lane == 0) { if constexpr (CG == 2) ptx::mbar_arrive_cluster(tmem_empty0 + acc * 8); else ptx::mbar_arrive(&tmem_empty[acc]); }
             }
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
@@ -670,8 +712,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================================================== hi/lo splitter (3xTF32): warps 12-15
         ptx::setmaxnreg_dec<48>();
         const int t = threadIdx.x - kSplitWarp0 * 32;   // 0..127
+        const uint32_t ready0 = CG == 2 ? ptx::mapa(ptx::smem_u32(&ready_bar[0]), 0) : 0u;   // the leader's `ready` barriers
         int s = 0; uint32_t ph = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int w = wid0; w < total_work; w += wstride) {
             const int split = w / num_tiles;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -692,7 +735,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     ptx::sts128(lo + i * 16, l);
                 }
                 ptx::fence_proxy_async_smem();
-                ptx::mbar_arrive(&ready_bar[s]);
+                if constexpr (CG == 2) ptx::mbar_arrive_cluster(ready0 + s * 8);
+                else ptx::mbar_arrive(&ready_bar[s]);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -700,9 +744,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     ptx::tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the pair still uses its smem / barriers
     if (warp == 2) {
         ptx::tcgen05_fence_after();
-        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (CG == 2) ptx::tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

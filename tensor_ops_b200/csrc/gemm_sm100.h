@@ -23,6 +23,7 @@ struct GemmCall {
     int split_k;    // 0 = choose automatically (only EPI_ATOMIC may split)
     int block_n;    // 0 = choose automatically, else 128 or 256
     int max_ctas;   // 0 = number of SMs
+    int cta_group;  // 0 = choose automatically, 1 = one CTA per tile, 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles)
     int accumulate; // EPI_ATOMIC only: add into out0 as it is (the caller zeroed it / is accumulating across calls)
     float* colsum;         // optional [N] fp32 accumulator, PRE-ZEROED by the caller: column sums of out0 (colsum_src 1) / out1 (2)
     int colsum_src;        // 0 = none

@@ -59,6 +59,7 @@ int main(int argc, char** argv) {
     int max_ctas = argc > 12 ? atoi(argv[12]) : 0;
     int chunk_kb = argc > 13 ? atoi(argv[13]) : 0;
     int no_tma = argc > 14 ? atoi(argv[14]) : 0;
+    int cg = argc > 15 ? atoi(argv[15]) : 0;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     unsigned int* wd_host; unsigned int* wd_dev;
     CK(cudaHostAlloc(&wd_host, 64, cudaHostAllocMapped)); wd_host[0] = wd_host[1] = 0;
@@ -88,7 +89,7 @@ int main(int argc, char** argv) {
     c.A = A; c.lda = lda; c.major_a = ma; c.B = B; c.ldb = ldb; c.major_b = mb;
     c.epi = epi; c.act = 0; c.alpha = 1.f; c.beta = 0.f; c.out0 = C; c.ld_out0 = N;
     c.bias = (epi == 2) ? bias : nullptr;
-    c.split_k = split; c.block_n = bn; c.max_ctas = max_ctas; c.chunk_kb = chunk_kb; c.no_tma_epilogue = no_tma;
+    c.split_k = split; c.block_n = bn; c.max_ctas = max_ctas; c.chunk_kb = chunk_kb; c.no_tma_epilogue = no_tma; c.cta_group = cg;
     char err[256] = {0};
     cudaStream_t st; CK(cudaStreamCreate(&st));
     auto run = [&]() {
@@ -140,7 +141,7 @@ int main(int argc, char** argv) {
     if (e != cudaSuccess) { printf("KERNEL FAIL (timing): %s watchdog code=0x%x\n", cudaGetErrorString(e), wd_host[0]); return 4; }
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= iters;
-    printf("RESULT dtype=%d passes=%d ma=%d mb=%d M=%d N=%d K=%d bn=%d epi=%d split=%d ctas=%d chunk=%d notma=%d : %.4f ms  %.1f TFLOP/s\n",
-           dtype, passes, ma, mb, M, N, K, bn, epi, split, max_ctas, chunk_kb, no_tma, ms, 2.0 * M * N * K / (ms * 1e-3) / 1e12);
+    printf("RESULT dtype=%d passes=%d ma=%d mb=%d M=%d N=%d K=%d bn=%d epi=%d split=%d ctas=%d chunk=%d notma=%d cg=%d : %.4f ms  %.1f TFLOP/s\n",
+           dtype, passes, ma, mb, M, N, K, bn, epi, split, max_ctas, chunk_kb, no_tma, cg, ms, 2.0 * M * N * K / (ms * 1e-3) / 1e12);
     return 0;
 }
