@@ -193,6 +193,12 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # stdout carries exactly ONE line (the JSON, rank 0): libraries that print to fd 1 (NCCL's "NCCL version ..." banner) are
+    # sent to stderr for the rest of the run, and the JSON line is written to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -369,7 +375,8 @@ def main():
         v, n, secs, threads = cpu_reference_rate(12.0, i, o)
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                                 "sample": f"{n} samples of the batch in {secs:.1f} s: per-sample hmatrix op sequence restated in NumPy/OpenBLAS fp32 (oracle.cpu_fflayer_step_reference), samples split over {threads} threads"}
-    print(json.dumps(line), flush=True)
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
