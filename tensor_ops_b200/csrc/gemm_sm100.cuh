@@ -337,15 +337,28 @@ __device__ __forceinline__ void stage_store_global(uint32_t buf, int lane, void*
     constexpr int ROWB = W * (int)sizeof(IO);
     constexpr int CPR = ROWB / 16;                 // 16-byte chunks per row
     constexpr int EPC = 16 / (int)sizeof(IO);      // elements per chunk
+    constexpr int RPI = 32 / CPR;                  // rows covered by one warp instruction
     const int j = lane % CPR, c = col + j * EPC;
-    IO* g0 = reinterpret_cast<IO*>(base) + (long long)(row0 + lane / CPR) * ld + c;
+    const int rl = lane / CPR;
+    IO* g0 = reinterpret_cast<IO*>(base) + (long long)(row0 + rl) * ld + c;
+    if (row0 + 32 <= M && col + W <= N) {          // interior block (warp-uniform): no guards, two swizzle variants at most
+        // rows rl + k*RPI.  128-byte rows: RPI = 4, the swizzle (r & 7) alternates between two values; 64-byte rows: RPI = 8, constant
+        const uint32_t s0 = buf + stage_off<ROWB>(rl, j);
+        const uint32_t s1 = buf + stage_off<ROWB>(rl + RPI, j);
+#pragma unroll
+        for (int k = 0; k < CPR; ++k) {
+            const uint32_t a = (ROWB == 128) ? ((k & 1) ? s1 : s0) + (k >> 1) * (2 * RPI * ROWB) : s0 + k * (RPI * ROWB);
+            *reinterpret_cast<uint4*>(g0 + (long long)k * RPI * ld) = ptx::lds128(a);
+        }
+        return;
+    }
     if (c >= N) return;
 #pragma unroll
     for (int k = 0; k < CPR; ++k) {
-        const int r = lane / CPR + k * (32 / CPR);
+        const int r = rl + k * RPI;
         if (row0 + r < M) {
             const uint4 u = ptx::lds128(buf + stage_off<ROWB>(r, j));
-            IO* g = g0 + (long long)k * (32 / CPR) * ld;
+            IO* g = g0 + (long long)k * RPI * ld;
             if (c + EPC <= N) {
                 *reinterpret_cast<uint4*>(g) = u;
             } else {
@@ -613,8 +626,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row = row0 + lane;
             const int ncols = min(HC, p.N - n0);                              // valid columns of this warp's half (may be <= 0)
             const int nblk = (row0 < p.M && ncols > 0) ? (ncols + W - 1) / W : 0;   // W-column blocks this warp owns in this tile
-            if (tma && nblk > 0 && epi_has_aux(p))                            // the first aux block does not depend on the accumulators
-                epi_issue_aux<T, W>(&tmAux, ew, lane, row0, n0);
+            if (tma && nblk > 0 && epi_has_aux(p)) {                          // the aux operand does not depend on the accumulators:
+                epi_issue_aux<T, W>(&tmAux, ew, lane, row0, n0);              // first block straight into the staging block,
+                if (lane > 0 && lane < nblk) ptx::tma_prefetch_l2_2d(&tmAux, n0 + lane * W, row0);   // the others into L2 meanwhile
+            }
             if constexpr (CG == 2) ptx::mbar_wait_cluster(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
             else ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
             ptx::tcgen05_fence_after();
@@ -660,8 +675,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m0 = (tile / p.num_n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (tile % p.num_n_tiles) * BN;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
-            if (tma && epi_has_aux(p) && m0 + q * 32 < p.M && n0 + half * HC < p.N)   // first aux block: requested before the K loop
+            if (tma && epi_has_aux(p) && m0 + q * 32 < p.M && n0 + half * HC < p.N) {   // first aux block: requested before the K loop
                 epi_issue_aux<float, 32>(&tmAux, ew, lane, m0 + q * 32, n0 + half * HC);
+                if (lane > 0 && lane < HC / 32 && n0 + half * HC + lane * 32 < p.N)       // the other blocks: into L2 during the K loop
+                    ptx::tma_prefetch_l2_2d(&tmAux, n0 + half * HC + lane * 32, m0 + q * 32);
+            }
             float sum[HC];
 #pragma unroll
             for (int e = 0; e < HC; ++e) sum[e] = 0.f;
@@ -691,15 +709,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
                 for (int c = 0; c < HC / 32; ++c) {
                     const int col = n0 + half * HC + c * 32;
-                    float v[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = sum[e];
-#pragma unroll
-                    for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];
+                    float (&v)[32] = *reinterpret_cast<float (*)[32]>(&sum[0]);   // the block is processed in place ...
                     if (col < p.N) {
                         if (tma) epi_block<float, 32, Cfg::EPI_SHARED>(p, &tmAux, ew, lane, row0, col, (c + 1 < HC / 32 && col + 32 < p.N) ? col + 32 : -1, v, loss_acc, wd);
                         else if (row < p.M) epi_direct<32>(p, row, col, vec, v, loss_acc);
                     }
+#pragma unroll
+                    for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];       // ... and the accumulators rotate afterwards
                 }
             }
         }

@@ -153,6 +153,10 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // all committed bulk stores of this thread are complete
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// bring a box into L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 // same, destination given as a shared-window address
 __device__ __forceinline__ void tma_load_2d_s(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
