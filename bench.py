@@ -55,6 +55,25 @@ def load_peaks():
     return dict(FALLBACK_PEAKS), "fallback"
 
 
+def ncu_traffic_bytes(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` summary
+    (profiles/r1_gemm_3xtf32_ncu.csv, captured with the same bench command); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_gemm_3xtf32_ncu.csv")
+    want = {"gemm_fwd": "<float, 0, 0,", "gemm_dW": "<float, 1, 1,", "gemm_dX": "<float, 0, 1,"}.get(tag)
+    if not want or not os.path.exists(path):
+        return None
+    try:
+        import csv
+        rows = {r[0]: r for r in csv.reader(open(path))}
+        names = rows["Kernel Name"][2:]
+        col = next(k for k, n in enumerate(names) if want in n)
+        rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        return float(rd[2 + col]) * scale.get(rd[1], 1.0) + float(wr[2 + col]) * scale.get(wr[1], 1.0)
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, 50 ms period)."""
 
@@ -349,8 +368,12 @@ def main():
     # fp32 configs run on the TF32 tensor pipe; no TF32 figure is in MEASURED_PEAKS.json, so peak = measured bf16 burst / 2
     # (TF32 dense is nominally half the bf16 rate on B200: 1.1 vs 2.25 PFLOP/s)
     peak = peaks["bf16_tflops"] / 2.0
+    passes = 3 if args.precision == "tf32x3" else 1
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": dom, "kernel_ms": dom_ms,
+                "traffic": ncu_traffic_bytes(dom), "kernel": dom, "kernel_ms": dom_ms,
+                "mma_flop_per_algorithmic_flop": passes, "tensor_pipe_frac": passes * achieved / peak,
+                "note": ("3xTF32 issues 3 tensor-core FLOP per algorithmic FLOP, so frac is capped at 1/3; tensor_pipe_frac = 3*frac is the share of the "
+                         "TF32 peak the MMA stream itself reaches") if passes == 3 else "single-pass TF32",
                 "peak_source": f"{peaks_src} bf16 burst {peaks['bf16_tflops']} TFLOP/s / 2 (TF32 = half the bf16 rate)",
                 "per_kernel_ms": {k: v["ms"] / v["launches"] for k, v in prof.items()},
                 "step_share": {k: v["ms"] / ms for k, v in prof.items()}}
@@ -360,6 +383,7 @@ def main():
             "config": {"workload": WORKLOAD, "i": i, "o": o, "batch_per_gpu": B, "global_batch": B * world,
                        "precision": {"tf32x3": "3xTF32 split on tcgen05 (fp32-grade, parity mode)", "tf32": "single-pass TF32 on tcgen05 (throughput mode, ~7e-4 rel err)", "simt": "fp32 FFMA"}[args.precision],
                        "parallelism": f"dp{world} (batch-sharded, one NCCL all-reduce of [dW||db] per step)" if world > 1 else "single GPU",
+                       "kernels": "3 per step: tcgen05 cta_group::2 GEMMs (CTA pairs, 256x256 tiles) with fused bias/logistic/dZ/db epilogue, split-K dW, dX",
                        "l2": "inputs larger than L2: X and dA are 256 MiB each per step vs 126 MB L2"},
             "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
             "algorithmic_flop_per_step": 6.0 * B * i * o, "tflops_step": 6.0 * B * i * o / (ms_per_step * 1e-3) / 1e12}

@@ -415,3 +415,19 @@ def test_host_buffer_entry_point_pipelined(ctx, B, n_chunks):
     close(g[:o * i].reshape(o, i), ref[2], 1e-5, "dW host path"); close(g[o * i:], ref[3], 1e-5, "db host path")
     # the device copy of the packed gradient is what a data-parallel run all-reduces
     assert np.array_equal(packed.numpy(), g)
+
+
+@pytest.mark.parametrize("prec", [tb.PREC_TF32X3, tb.PREC_TF32])
+@pytest.mark.parametrize("B", [129, 255, 257, 385, 512])
+def test_cta_pair_tile_edges(ctx, prec, B):
+    """Row counts around the 128/256-row boundaries of the CTA-pair (cta_group::2) tiles: the peer CTA of the last pair owns
+    1, 127, 1 (+ a full pair), ... valid rows; o = 264 also makes dW's own M straddle a pair boundary."""
+    ctx.set_precision(prec)
+    rng = np.random.default_rng(B)
+    i, o = 200, 264
+    X = rng.uniform(-1, 1, (B, i)); W = rng.normal(0, 0.5, (o, i)); b = rng.normal(0, 0.5, o); dA = rng.normal(size=(B, o))
+    X, W, b, dA = (a.astype(np.float32).astype(np.float64) for a in (X, W, b, dA))
+    ref = O.fflayer_logistic_dense(X, W, b, dA)
+    got = nn.fflayer_fwd_grad(ctx.from_numpy(X), ctx.from_numpy(W), ctx.from_numpy(b), ctx.from_numpy(dA))
+    for name, t, r in zip(("A", "dX", "dW", "db"), got, ref):
+        close(t, r, TOL[prec], f"{name} B={B}")
