@@ -573,6 +573,182 @@ def trainNetwork(loss: TOp, r, x, y, n: Network) -> Network:
 
 
 # --------------------------------------------------------------------------------------------
+# auto-encoders (src/TensorOps/Learn/NeuralNet/AutoEncoder.hs) — SURVEY §8-f4
+# --------------------------------------------------------------------------------------------
+
+
+@dataclass
+class Encoder:
+    """`Encoder t i o = E { eEncoder :: Network t i o, eDecoder :: Network t o i }` (AutoEncoder.hs:36-39)."""
+    enc: Network
+    dec: Network
+
+
+def encoderNet(e: Encoder) -> Network:
+    """`encoderNet (E e d) = e >>> d` (AutoEncoder.hs:80-84; `>>>` on Networks is `~*~`)."""
+    return net_compose(e.enc, e.dec)
+
+
+def encode(e: Encoder, x): return runNetwork(e.enc, x)             # AutoEncoder.hs:41-47
+def decode(e: Encoder, h): return runNetwork(e.dec, h)             # AutoEncoder.hs:49-55
+def encodeDecode(e: Encoder, x): return runNetwork(encoderNet(e), x)   # AutoEncoder.hs:57-62
+
+
+def _encoder_loss_op(loss: TOp, net: Network) -> TOp:
+    """firstOp duplicate >>> secondOp @'[ '[i] ] o >>> swap >>> loss   (AutoEncoder.hs:72-78, 129-138): the input is both
+    the network's input and the loss target."""
+    return firstOp(op_duplicate(), len(net.params)) >> secondOp(1, net.op) >> op_swap() >> loss
+
+
+def testEncoder(loss: TOp, e: Encoder, x) -> float:
+    """AutoEncoder.hs:64-78."""
+    net = encoderNet(e)
+    return float(runTOp(_encoder_loss_op(loss, net), [x] + net.params)[0])
+
+
+def encGrad(loss: TOp, x, e: Encoder):
+    """`encGrad` (AutoEncoder.hs:110-142): gradients of the reconstruction loss w.r.t. (encoder params, decoder params)."""
+    net = encoderNet(e)
+    gr = gradTOp(_encoder_loss_op(loss, net), [x] + net.params)[1:]
+    nE = len(e.enc.params)
+    return gr[:nE], gr[nE:]
+
+
+def trainEncoder(loss: TOp, r, x, e: Encoder) -> Encoder:
+    """`trainEncoder` (AutoEncoder.hs:86-108): p' = p - r*g on both halves."""
+    gE, gD = encGrad(loss, x, e)
+    rr = e.enc.params[0].dtype.type(r)
+    return Encoder(Network(e.enc.op, [p - rr * g for p, g in zip(e.enc.params, gE)]),
+                   Network(e.dec.op, [p - rr * g for p, g in zip(e.dec.params, gD)]))
+
+
+# --------------------------------------------------------------------------------------------
+# recurrent networks (src/TensorOps/Learn/NeuralNet/Recurrent.hs) — SURVEY §8-f4
+# --------------------------------------------------------------------------------------------
+
+
+def op_shuffle(idx: Sequence[int], n_in: int) -> TOp:
+    """`shuffle` (TOp.hs:106-134): output j = input idx[j]; the cotangent of input i is the sum of the cotangents of every
+    output that selected it (zeros if none did)."""
+    def g(xs, ds):
+        out = []
+        for i in range(n_in):
+            picks = [d for j, d in zip(idx, ds) if j == i]
+            out.append(sumT(picks) if picks else np.zeros_like(xs[i]))
+        return out
+    return TOp(lambda xs: [xs[j] for j in idx], g, n_in, len(idx))
+
+
+def op_swap_(nN: int, nM: int) -> TOp:
+    """`swap'` (TOp.hs:353-357): (ns ++ ms) -> (ms ++ ns)."""
+    return op_shuffle(list(range(nN, nN + nM)) + list(range(nN)), nN + nM)
+
+
+def op_drop(n: int, n_in: int) -> TOp:
+    """`drop` (TOp.hs:359-369)."""
+    return op_shuffle(list(range(n, n_in)), n_in)
+
+
+def op_take(n: int, n_in: int) -> TOp:
+    """`take` (TOp.hs:371-381)."""
+    return op_shuffle(list(range(n)), n_in)
+
+
+def op_add3() -> TOp:
+    """`add3` (TOp.hs:222-229)."""
+    return TOp(lambda xs: [sumT(xs)], lambda xs, ds: [ds[0]] * 3, 3, 1)
+
+
+@dataclass
+class RNetwork:
+    """`Network t i o = N { _nOp :: TOp ('[i] : ss ++ ps) ('[o] : ss), _nState :: Prod t ss, _nParams :: Prod t ps }`
+    (Recurrent.hs:69-75)."""
+    op: TOp
+    state: Prod
+    params: Prod
+
+
+def r_fullyConnected(i: int, o: int, act: Callable[[], TOp], rng: np.random.Generator, dtype=np.float64) -> RNetwork:
+    """`fullyConnected` (Recurrent.hs:97-125): y = W x + W' h + b is the OUTPUT, act(y) the new state.  Draw order s, w, w', b;
+    parameter order (w', w, b)."""
+    s = rng.normal(0.0, 0.5, size=(o,)).astype(dtype)
+    w = rng.normal(0.0, 0.5, size=(o, i)).astype(dtype)
+    w_ = rng.normal(0.0, 0.5, size=(o, o)).astype(dtype)
+    b = rng.normal(0.0, 0.5, size=(o,)).astype(dtype)
+    fc = (secondOp(1, firstOp(op_swap() >> op_matVec(), 2) >> firstOp(op_swap(), 1))
+          >> firstOp(op_swap() >> op_matVec(), 2)
+          >> op_add3()
+          >> op_duplicate()
+          >> secondOp(1, act()))
+    return RNetwork(fc, [s], [w_, w, b])
+
+
+def r_stateless(n: Network) -> RNetwork:
+    """`stateless` (Recurrent.hs:127-137)."""
+    return RNetwork(n.op, [], list(n.params))
+
+
+def r_then_act(n: RNetwork, f: TOp) -> RNetwork:
+    """`(*~)` (Recurrent.hs:262-267): o >>> firstOp f."""
+    return RNetwork(n.op >> firstOp(f, len(n.state)), n.state, n.params)
+
+
+def r_compose(n1: RNetwork, n2: RNetwork) -> RNetwork:
+    """`(~*~)` (Recurrent.hs:178-233): states ss2 ++ ss1, parameters ps1 ++ ps2."""
+    s1, p1, s2, p2 = len(n1.state), len(n1.params), len(n2.state), len(n2.params)
+    o = (secondOp(1, firstOp(op_swap_(s2, s1 + p1), p2))
+         >> firstOp(n1.op, s2 + p2)
+         >> secondOp(1, op_swap_(s1, s2 + p2))
+         >> firstOp(n2.op, s1))
+    return RNetwork(o, n2.state + n1.state, n1.params + n2.params)
+
+
+def r_runNetwork(n: RNetwork, x):
+    """`runNetwork` (Recurrent.hs:235-244): returns (output, network with the new state)."""
+    out = runTOp(n.op, [x] + n.state + n.params)
+    return out[0], RNetwork(n.op, out[1:], n.params)
+
+
+def r_unroll(nS: int, nP: int, o: TOp, n: int) -> TOp:
+    """`unroll` (Recurrent.hs:392-431): TOp (Replicate n '[i] ++ ss ++ ps) (ss ++ Replicate n '[o]).  The step is applied to the
+    LAST input of the list first, and its output is appended LAST — so with inputs in reverse time order (netGrad passes
+    `reverse xs`) the outputs come out in reverse time order too."""
+    if n == 0:
+        return op_take(nS, nS + nP)
+    m = n - 1
+    step = fanout(o, op_drop(1 + nS, 1 + nS + nP)) >> op_swap_(1, nS + nP)      # (x, ss, ps) -> (ss', ps, y)
+    return secondOp(m, step) >> firstOp(r_unroll(nS, nP, o, m), 1)
+
+
+def r_rollup(loss: TOp, n: int) -> TOp:
+    """`rollup` (Recurrent.hs:434-463): TOp (Replicate n '[o] ++ Replicate n '[o]) '[ '[] ] — the LAST output is paired with the
+    FIRST target, and the per-step losses are added."""
+    if n == 0:
+        return op_konst([()], 0.0)
+    if n == 1:
+        return loss
+    m = n - 1
+    return secondOp(m, firstOp(loss, m) >> op_swap_(1, m)) >> firstOp(r_rollup(loss, m), 1) >> op_add()
+
+
+def r_netGrad(loss: TOp, xs: Sequence[np.ndarray], ys: Sequence[np.ndarray], n: RNetwork):
+    """`netGrad` (Recurrent.hs:277-324): back-propagation through time by unrolling.  Returns (input gradients, state gradients,
+    parameter gradients); as in the reference the input gradients are in the order of `reverse xs` (the reference converts the
+    gradient Prod of the reversed inputs back to a Vec without re-reversing it)."""
+    T, nS, nP = len(xs), len(n.state), len(n.params)
+    unrolled = r_unroll(nS, nP, n.op, T) >> op_drop(nS, nS + T)
+    full = firstOp(unrolled, T) >> r_rollup(loss, T)
+    grad = gradTOp(full, list(xs)[::-1] + n.state + n.params + list(ys))[:T + nS + nP]
+    return grad[:T], grad[T:T + nS], grad[T + nS:]
+
+
+def r_trainNetwork(loss: TOp, rS, rP, xs, ys, n: RNetwork) -> RNetwork:
+    """`trainNetwork'` (Recurrent.hs:326-352): separate rates for the initial state and the parameters."""
+    _, gS, gP = r_netGrad(loss, xs, ys, n)
+    return RNetwork(n.op, [s - s.dtype.type(rS) * g for s, g in zip(n.state, gS)], [p - p.dtype.type(rP) * g for p, g in zip(n.params, gP)])
+
+
+# --------------------------------------------------------------------------------------------
 # batched semantics fixed by SURVEY §8(d): per-sample runTOp + gradTOp', parameter grads summed
 # --------------------------------------------------------------------------------------------
 

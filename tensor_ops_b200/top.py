@@ -234,6 +234,11 @@ def shuffle(idx: Sequence[int], n_in: int) -> TOp:
     return TOp(lambda T, xs: [xs[j] for j in idx], g, n_in, len(idx), ("shuffle", tuple(idx)))
 
 
+def swap_(nN: int, nM: int) -> TOp:
+    """`swap'` (TOp.hs:353-357): (ns ++ ms) -> (ms ++ ns)."""
+    return shuffle(list(range(nN, nN + nM)) + list(range(nN)), nN + nM)
+
+
 def drop(n: int, n_in: int) -> TOp:
     """`drop` (TOp.hs:359-369)."""
     return shuffle(list(range(n, n_in)), n_in)
