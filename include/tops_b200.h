@@ -165,6 +165,14 @@ int tops_fflayer_fwd_grad(tops_ctx*, const tops_buf* X, const tops_buf* W, const
  * gradient is also copied there and the call synchronises.  A / dX (device, may be NULL slots) receive the per-sample outputs. */
 int tops_fflayer_fwd_grad_host(tops_ctx*, const float* X_host, const float* dA_host, int64_t B, const tops_buf* W, const tops_buf* b,
                                int act, int n_chunks, tops_buf** A, tops_buf** dX, tops_buf** grads, float* grads_host);
+/* Data-parallel forward + VJP with the parameter-gradient all-reduce fused into the dW GEMM.  `grads_mc` is the NVLS multicast
+ * alias of a packed fp32 buffer [dW (o*i) || db (o)] that every rank has bound to one multicast object (e.g. torch symmetric
+ * memory's multicast_ptr).  Split-K partials are summed locally into `grads_local` (same packing); the last partial to finish a
+ * region of a dW tile pushes the finished region once with multimem.red, so the NVSwitch sums it into every rank's replica while
+ * the GEMM is still running; db is pushed by a tiny kernel.  Caller protocol per step: zero the symmetric replica, barrier, this
+ * call, barrier.  (The reference has no parallelism; this completes the sum over samples its training fold performs serially.) */
+int tops_fflayer_fwd_grad_mc(tops_ctx*, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act, const tops_buf* dA,
+                             tops_buf** A, tops_buf** dX, tops_buf** grads_local, void* grads_mc);
 /* netGrad (FeedForward.hs:178-199) of a genNet-style network (FeedForward.hs:216-235) over a batch:
  *   layers l = 0..n-1 with W[l], b[l], acts[l]; loss on (A_out, Y); per-sample losses summed into loss_sum (rank 0).
  *   Outputs: A_out[B,o], loss_sum[], dX[B,i] (may be NULL to skip), dW[l], db[l]. */

@@ -204,6 +204,7 @@ int run_gemm(tops_ctx* ctx, GemmCall c) {
         if (r > 0) return set_err(ctx, TOPS_ERR_CUDA, "%s", err);
         if (c.dtype == 1) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "bf16 gemm needs 16-byte aligned operands with strides that are multiples of 8 elements (%s)", err);
     }
+    if (c.out0_mc) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "the fused all-reduce needs the tcgen05 GEMM: 16-byte aligned operands and rows");
     int r = k::gemm_simt(lc_of(ctx), c);
     if (r != 0) return set_err(ctx, TOPS_ERR_CUDA, "simt gemm launch failed (%d)", r);
     return TOPS_OK;
@@ -802,13 +803,23 @@ int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, 
     return run_gemm(ctx, g);
 }
 // dW = dZ^T Xin   (split-K over the batch, fp32 atomics into a zeroed output), db = column sums of dZ
-int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, float* dW, float* db, bool db_done = false, bool accumulate = false) {
+int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, float* dW, float* db, bool db_done = false, bool accumulate = false,
+          float* dW_mc = nullptr) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.o; g.N = (int)s.i; g.K = (int)s.B;
     g.A = dZ; g.lda = s.o; g.major_a = MAJOR_MN;
     g.B = Xin; g.ldb = s.i; g.major_b = MAJOR_MN;
     g.epi = EPI_ATOMIC; g.alpha = 1.f; g.out0 = dW; g.ld_out0 = s.i; g.tag = "gemm_dW"; g.accumulate = accumulate ? 1 : 0;
-    TRY(run_gemm(ctx, g));
+    int* counters = nullptr;
+    if (dW_mc) {   // fused all-reduce: region-arrival counters for the "last split pushes the finished region" protocol
+        const size_t n = ((size_t)(s.o + 127) / 128 + 1) * ((size_t)(s.i + 127) / 128 + 1) * 8 + 16;   // >= tiles * CTAs per tile * 8 epilogue warps
+        CUDA_TRY(ctx, cudaMallocAsync((void**)&counters, n * sizeof(int), ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, n * sizeof(int), ctx->stream));
+        g.out0_mc = dW_mc; g.tile_counters = counters;
+    }
+    int rc_ = run_gemm(ctx, g);
+    if (counters) cudaFreeAsync(counters, ctx->stream);
+    TRY(rc_);
     if (db && !db_done && accumulate) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "accumulating db needs the fused column sums (aligned fp32/bf16 rows)");
     if (db && !db_done) {
         ProfScope prof_(ctx, "col_sums_db", 0.0, (s.dtype == TOPS_BF16 ? 2.0 : 4.0) * (double)s.B * s.o);
@@ -918,6 +929,36 @@ extern "C" int tops_fflayer_fwd_grad_host(tops_ctx* ctx, const float* X_host, co
         CUDA_TRY(ctx, cudaMemcpyAsync(grads_host, dW, sizeof(float) * (size_t)(o * i + o), cudaMemcpyDeviceToHost, ctx->stream));
         return tops_sync(ctx);
     }
+    return TOPS_OK;
+}
+
+// Data-parallel forward + VJP with the gradient all-reduce FUSED into the dW GEMM (NVLS): `grads_mc` is the multicast alias of a
+// packed [dW (o*i) || db (o)] buffer that every rank of the job has bound (torch symmetric memory).  Split-K partials of dW are
+// summed locally (`grads_local`); the last partial to finish a 32-row region of a tile pushes the finished region once with
+// multimem.red — the NVSwitch adds it into every rank's replica while the remaining tiles are still being computed.  db (o floats)
+// is pushed by a tiny kernel right after the forward GEMM.  No separate all-reduce pass over dW exists.
+// Protocol (caller): zero the symmetric replica, barrier (all replicas zeroed), this call, barrier (all reductions landed).
+extern "C" int tops_fflayer_fwd_grad_mc(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act, const tops_buf* dA,
+                                        tops_buf** A, tops_buf** dX, tops_buf** grads_local, void* grads_mc) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    LayerShapes s; TRY(layer_shapes(ctx, X, W, b, &s)); TRY(check_act(ctx, act));
+    if (!grads_mc || (reinterpret_cast<uintptr_t>(grads_mc) & 15) != 0) return set_err(ctx, TOPS_ERR_INVALID, "fflayer_fwd_grad_mc: multicast pointer must be non-NULL and 16-byte aligned");
+    if (!dA || dA->rank != 2 || dA->dims[0] != s.B || dA->dims[1] != s.o || dA->dtype != s.dtype || dA->tr) return set_err(ctx, TOPS_ERR_SHAPE, "fflayer: dA[B,o] expected");
+    if (!grads_local) return set_err(ctx, TOPS_ERR_INVALID, "fflayer_fwd_grad_mc: NULL grads_local slot");
+    int64_t dAo[2] = {s.B, s.o}, dXs[2] = {s.B, s.i}, g_[1] = {s.o * s.i + s.o};
+    TRY(prep_out(ctx, A, s.dtype, 2, dAo));
+    if (dX) TRY(prep_out(ctx, dX, s.dtype, 2, dXs));
+    TRY(prep_out(ctx, grads_local, TOPS_F32, 1, g_));
+    float* dW = (float*)(*grads_local)->data; float* db = dW + s.o * s.i;
+    float* dW_mc = (float*)grads_mc; float* db_mc = dW_mc + s.o * s.i;
+    Tmp tmp; tops_buf* dZ = nullptr;
+    TRY(alloc_buf(ctx, s.dtype, 2, dAo, &dZ)); tmp.keep(dZ);
+    int db_fused = 0;
+    TRY(fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, (*A)->data, dA->data, dZ->data, nullptr, db, &db_fused));
+    TRY(dw_db(ctx, s, dZ->data, X->data, dW, db, db_fused != 0, false, dW_mc));
+    k::mc_push(lc_of(ctx), db, db_mc, s.o);            // o floats: the bias gradient joins the same multicast buffer
+    TRY(check_launch(ctx, "mc_push"));
+    if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
     return TOPS_OK;
 }
 

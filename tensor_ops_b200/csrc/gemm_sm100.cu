@@ -179,6 +179,8 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     // fused column sums ride on the staged blocks of the TMA epilogue; tell the caller whether they were produced
     p.colsum = (tma_epi && c.colsum_src != 0) ? c.colsum : nullptr;
     p.colsum_src = c.colsum_src;
+    p.out0_mc = c.epi == EPI_ATOMIC ? c.out0_mc : nullptr; p.tile_counters = c.tile_counters;
+    if (p.out0_mc && !p.tile_counters) return fail(-1, "gemm: out0_mc needs tile_counters");
     if (c.colsum_fused) *c.colsum_fused = p.colsum != nullptr ? 1 : 0;
     auto vec_ok = [&](const void* ptr, long long ld) {
         if (!ptr) return true;

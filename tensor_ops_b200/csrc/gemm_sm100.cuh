@@ -59,6 +59,11 @@ struct GemmParams {
     float* loss;              // scalar accumulator (EPI_BIAS_ACT_SE)
     float* colsum;            // optional [N] accumulator (pre-zeroed): column sums of out0 (colsum_src = 1) or out1 (= 2), TMA epilogue only
     int colsum_src;
+    // Fused all-reduce (EPI_ATOMIC only): split-K partials are summed locally in out0; the LAST partial to finish a region
+    // (counted in tile_counters) pushes the finished region once to the NVLS multicast alias out0_mc with multimem.red, so the
+    // NVSwitch adds it into every rank's replica while the rest of the GEMM is still running.
+    float* out0_mc;
+    int* tile_counters;       // [num_tiles * CG * 8] zeroed by the caller
     int io_bf16;              // out0/out1/aux0 are bf16 (bf16 pipelines); 0 = fp32
     int vec_ok;               // 16-byte vector access legal for out0/out1/aux0
     int tma_epi;              // epilogue I/O goes through smem staging + TMA (tensor maps tmO0/tmO1/tmAux are valid)
@@ -370,6 +375,34 @@ __device__ __forceinline__ void stage_store_global(uint32_t buf, int lane, void*
     }
 }
 
+// Fused all-reduce of split-K partials: called by an epilogue warp after its local reds for one region (32 rows x `ncols` columns
+// starting at (row0, col0)) of one work item.  The warp that completes the region last (all split_k partials are in) re-reads the
+// finished sums from L2 and pushes them ONCE to the multicast alias: the switch adds them into every rank's gradient buffer.
+__device__ __forceinline__ void mc_push_region_if_last(const GemmParams& p, int counter_idx, int lane, int row0, int col0, int ncols) {
+    __threadfence();                                   // this lane's reds are performed before the arrival is counted
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(p.tile_counters + counter_idx, 1) == p.split_k - 1) ? 1 : 0;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();                                   // acquire: the other partials' reds (performed at L2) are visible to the loads below
+    const float* src = reinterpret_cast<const float*>(p.out0);
+    const bool vec = (reinterpret_cast<uintptr_t>(p.out0) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out0_mc) & 15) == 0 && (p.ld_out0 & 3) == 0 && (col0 & 3) == 0;
+    for (int r = 0; r < 32; ++r) {
+        const int row = row0 + r;
+        if (row >= p.M) break;
+        const long long base = (long long)row * p.ld_out0 + col0;
+        for (int c = lane * 4; c < ncols; c += 128) {
+            if (vec && c + 4 <= ncols) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + base + c));
+                ptx::multimem_red_add_v4(p.out0_mc + base + c, v.x, v.y, v.z, v.w);
+            } else {
+                for (int e = 0; e < 4 && c + e < ncols; ++e) ptx::multimem_red_add(p.out0_mc + base + c + e, __ldcg(src + base + c + e));
+            }
+        }
+    }
+}
+
 // Per-warp state of the staged epilogue.  The aux operand (dA / target / previous activation / C) arrives by TMA into
 // `aux_buf`; outputs are transposed through `out_buf` (== aux_buf in the 3-pass kernel, which has one block per warp).
 struct EpiWarp {
@@ -649,6 +682,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) { if constexpr (CG == 2) ptx::mbar_arrive_cluster(tmem_empty0 + acc * 8); else ptx::mbar_arrive(&tmem_empty[acc]); }
+            if (p.epi == EPI_ATOMIC && p.out0_mc != nullptr && nblk > 0)
+                mc_push_region_if_last(p, (tile * CG + (int)cta_rank) * 8 + (warp - 4), lane, row0, n0, ncols);
         }
         if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {
 #pragma unroll
@@ -717,6 +752,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];       // ... and the accumulators rotate afterwards
                 }
+                if (p.epi == EPI_ATOMIC && p.out0_mc != nullptr && n0 + half * HC < p.N)
+                    mc_push_region_if_last(p, (tile * CG + (int)cta_rank) * 8 + (warp - 4), lane, row0, n0 + half * HC, min(HC, p.N - (n0 + half * HC)));
             }
         }
         if (p.epi == EPI_BIAS_ACT_SE && p.loss != nullptr) {

@@ -28,6 +28,8 @@ struct GemmCall {
     float* colsum;         // optional [N] fp32 accumulator, PRE-ZEROED by the caller: column sums of out0 (colsum_src 1) / out1 (2)
     int colsum_src;        // 0 = none
     int* colsum_fused;     // out: set to 1 if the kernel produced the column sums (TMA epilogue), else 0 (caller reduces separately)
+    float* out0_mc;        // EPI_ATOMIC only: NVLS multicast alias of a buffer shaped like out0; finished split-K regions are pushed there once
+    int* tile_counters;    // with out0_mc: zeroed int[ceil(M/128) * ceil(N/bn) * 8 + 16] region-arrival counters
     int no_tma_epilogue;   // 1 = force the direct register<->global epilogue (bring-up / A-B comparison)
     int chunk_kb;   // 3-pass only: k-blocks per TMEM chunk before promotion to fp32 registers (0 = default 4)
     const char* tag;   // profiling label (tops_profile_*), may be NULL

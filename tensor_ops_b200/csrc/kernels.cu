@@ -477,6 +477,18 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const float* __restrict__ A, 
 }  // namespace
 
 // ====================================================================== launch wrappers
+namespace {
+__global__ void k_mc_push(const float* __restrict__ src, float* out_mc, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) ptx::multimem_red_add(out_mc + i, src[i]);
+}
+}  // namespace
+void mc_push(const LaunchCtx& lc, const float* src, float* out_mc, int64_t n) {
+    if (n <= 0) return;
+    k_mc_push<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(src, out_mc, n);
+    count(lc);
+}
+
 void fill(const LaunchCtx& lc, float* p, int64_t n, float v) { if (n <= 0) return; k_fill<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(p, n, v); count(lc); }
 void fill_bf16(const LaunchCtx& lc, void* p, int64_t n, float v) { if (n <= 0) return; k_fill_bf16<<<grid_for(lc, n), kThreads, 0, lc.stream>>>((__nv_bfloat16*)p, n, v); count(lc); }
 void rand_normal(const LaunchCtx& lc, float* p, int64_t n, float mean, float sd, uint64_t seed) { if (n <= 0) return; k_rand<true><<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(p, n, mean, sd, seed); count(lc); }

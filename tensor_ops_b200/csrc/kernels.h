@@ -35,6 +35,9 @@ void bias_act(const LaunchCtx&, int act, const float* Z, const float* bias, floa
 struct LiftProgram { int len; int n_consts; int32_t code[64]; float consts[16]; };
 void lift(const LaunchCtx&, const LiftProgram& prog, int n_in, const float* const* in, float* out, int64_t n);
 
+// out_mc[i] (+)= src[i] in EVERY replica bound to the NVLS multicast address out_mc (multimem.red); n fp32 elements
+void mc_push(const LaunchCtx&, const float* src, float* out_mc, int64_t n);
+
 // ---- reductions (deterministic two-stage)
 void sum_all(const LaunchCtx&, const float* x, int64_t n, float* out_scalar, float* workspace /* >= 1024 floats */);
 void dot(const LaunchCtx&, const float* x, const float* y, int64_t n, float* out_scalar, float* workspace);

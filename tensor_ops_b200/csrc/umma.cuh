@@ -293,6 +293,15 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+// NVLink SHARP (NVLS): a reduction pushed ONCE to a multicast address is added by the NVSwitch into the replica of every GPU
+// bound to the multicast object — the all-reduce of split-K partials happens in the switch, tile by tile, from the GEMM epilogue
+__device__ __forceinline__ void multimem_red_add_v4(float* mc_addr, float a, float b, float c, float d) {
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void multimem_red_add(float* mc_addr, float a) {
+    asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc_addr), "f"(a) : "memory");
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

@@ -63,3 +63,35 @@ def allreduce_sum_(packed_torch, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(packed_torch, op=dist.ReduceOp.SUM, group=group)
     return packed_torch
+
+
+class FusedGradAllReduce:
+    """The packed gradient buffer as NVLS symmetric memory: every rank allocates the same buffer, binds it to one multicast
+    object (torch.distributed._symmetric_memory) and hands the MULTICAST address to `tops_fflayer_fwd_grad_mc`, whose GEMM
+    epilogues emit `multimem.red` — the NVSwitch adds each split-K partial into every rank's replica while the GEMMs run, so the
+    data-parallel all-reduce has no pass of its own.  Per step: `begin()` (zero + barrier), the fused call, `end()` (barrier).
+    Raises RuntimeError when the platform has no multicast support (callers fall back to `allreduce_sum_`)."""
+
+    def __init__(self, numel: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("FusedGradAllReduce needs an initialised process group")
+        group = group or dist.group.WORLD
+        self.local = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        self.local.zero_()
+        self.handle = symm_mem.rendezvous(self.local, group)
+        self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if self.multicast_ptr == 0:
+            raise RuntimeError("symmetric memory came up without a multicast pointer (no NVLS on this platform)")
+        self.world = dist.get_world_size(group)
+
+    def begin(self):
+        """Zero the local replica and wait until every rank has done so (nobody's reductions may land in a stale buffer)."""
+        self.local.zero_()
+        self.handle.barrier(channel=0)
+
+    def end(self):
+        """All ranks' multimem reductions have been issued and completed: the local replica now holds the summed gradient."""
+        self.handle.barrier(channel=1)

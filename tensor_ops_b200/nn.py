@@ -195,6 +195,31 @@ def fflayer_fwd_grad(X: CuTensor, W: CuTensor, b: CuTensor, dA: CuTensor, act: i
     return tuple(res)
 
 
+def fflayer_fwd_grad_mc(X: CuTensor, W: CuTensor, b: CuTensor, dA: CuTensor, grads_multicast_ptr: int, act: int = L.ACT_LOGISTIC,
+                        want_dx: bool = True, out: Optional[Sequence[Optional[CuTensor]]] = None):
+    """Data-parallel runTOp + gradTOp' with the gradient all-reduce fused into the dW GEMM (tops_fflayer_fwd_grad_mc): finished
+    dW regions and db leave the device as NVLS multimem reductions into the packed buffer behind `grads_multicast_ptr` (see
+    dp.FusedGradAllReduce for the begin/end protocol).  Returns (A, dX, grads_local); `out` may hold pre-allocated tensors for
+    them (grads_local: this rank's own packed [dW‖db] sum, o*i + o floats)."""
+    ctx = X.ctx
+    slots = [L.c_buf(), L.c_buf(), L.c_buf()]
+    if out is not None:
+        for j, t in enumerate(out):
+            if t is not None:
+                slots[j] = L.c_buf(t.b.value)
+    ctx.check(L.lib.tops_fflayer_fwd_grad_mc(ctx.h, X.b, W.b, b.b, act, dA.b, C.byref(slots[0]), C.byref(slots[1]) if want_dx else None,
+                                             C.byref(slots[2]), C.c_void_p(grads_multicast_ptr)))
+    res = []
+    for j in range(3):
+        if out is not None and j < len(out) and out[j] is not None:
+            res.append(out[j])
+        elif j == 1 and not want_dx:
+            res.append(None)
+        else:
+            res.append(CuTensor(ctx, slots[j]))
+    return tuple(res)
+
+
 def fflayer_fwd_grad_host(ctx: Context, X_host, W: CuTensor, b: CuTensor, dA_host, act: int = L.ACT_LOGISTIC, grads_out=None,
                           allreduce: Optional[Callable[[], None]] = None, workspace=None, n_chunks: int = 0):
     """Host-buffer entry point of the batched fwd+grad (tops_fflayer_fwd_grad_host): `fromList` the batch (X, dA: C-contiguous

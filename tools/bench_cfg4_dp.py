@@ -26,7 +26,15 @@ A = ctx.empty((B, n), L.BF16); dX = ctx.empty((B, n), L.BF16)
 layout = dp.PackedLayout.for_layers([(n, n)])
 packed_t = torch.zeros(layout.numel, dtype=torch.float32, device=dev); packed = ctx.wrap_torch(packed_t)
 dWv, dbv = layout.views(packed)
+fused = None
+local_grads = ctx.empty((layout.numel,))
+if world > 1 and "--nccl" not in sys.argv:
+    try: fused = dp.FusedGradAllReduce(layout.numel, dev)
+    except Exception as exc: print("fused all-reduce unavailable:", exc, file=sys.stderr)
 def step(comm=True):
+    if comm and fused is not None:          # all-reduce fused into the dW / db epilogues (NVLS multimem.red)
+        fused.begin(); nn.fflayer_fwd_grad_mc(X, W, b, dA, fused.multicast_ptr, out=(A, dX, local_grads)); fused.end()
+        return
     nn.fflayer_fwd_grad(X, W, b, dA, out=(A, dX, dWv, dbv))
     if comm: dp.allreduce_sum_(packed_t)
 def barrier():
@@ -52,6 +60,7 @@ if rank == 0:
     flop = 6.0 * Bg * n * n
     real_stdout.write(json.dumps({"config": 4, "n_gpus": world, "scaling": "strong", "global_batch": Bg, "rows_per_gpu": B, "ms_per_step": ms,
                                   "ms_per_step_without_allreduce": ms_nocomm, "samples_per_s": Bg / ms * 1e3, "tflops_algorithmic_per_gpu": flop / world / ms / 1e9,
-                                  "frac_of_measured_bf16_peak": flop / world / ms / 1e9 / peak, "allreduce_bytes": layout.numel * 4}) + "\n")
+                                  "frac_of_measured_bf16_peak": flop / world / ms / 1e9 / peak, "allreduce_bytes": layout.numel * 4,
+                                  "allreduce": "fused NVLS multimem.red in the GEMM epilogues" if fused is not None else "NCCL"}) + "\n")
     real_stdout.flush()
 if world > 1: dist.destroy_process_group()
