@@ -300,12 +300,12 @@ def main():
                 return float(t.item())
             t_nccl, t_fused = quick(step_nccl), quick(step_fused)
             allreduce_trial = {"nccl_ms_per_step": t_nccl, "fused_ms_per_step": t_fused}
-            if t_fused < t_nccl or args.allreduce == "fused":
+            if t_fused < 0.97 * t_nccl or args.allreduce == "fused":   # a clear win only: both paths synchronise the ranks, trials are noisy
                 step = step_fused
                 allreduce_kind = "fused: finished dW regions are pushed from the GEMM epilogue with NVLS multimem.red into symmetric memory (checked against NCCL on this run)"
                 packed_t, packed = fused.local, ctx.wrap_torch(fused.local)
             else:
-                allreduce_kind += " (the fused NVLS push was verified but measured slower on this workload)"
+                allreduce_kind += " (the fused NVLS push was verified on this run but is not clearly faster on this workload)"
 
     def barrier():
         torch.cuda.synchronize()
