@@ -81,6 +81,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop_evt = threading.Event()
+        self.active = True   # cleared while the host prepares buffers between timed regions (idle clocks are not load)
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -97,6 +98,9 @@ class ClockSampler(threading.Thread):
         names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80,
                  "sw_power_cap": 0x4, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
         while not self._stop_evt.is_set():
+            if not self.active:
+                self._stop_evt.wait(0.002)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -329,10 +333,11 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    if sampler:
+        sampler.active = False
     prof = ctx.profile_summary()
     ctx.profile(False)
     launches = ctx.launch_count() - n0
-    clocks = sampler.stop() if sampler else None
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -349,11 +354,15 @@ def main():
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.profile(True)
+        if sampler:
+            sampler.active = True
         s0.record()
         for _ in range(args.steps):
             step()
         s1.record()
         barrier()
+        if sampler:
+            sampler.active = False
         sms = s0.elapsed_time(s1) / args.steps
         sprof = ctx.profile_summary()
         ctx.profile(False)
@@ -384,11 +393,15 @@ def main():
         barrier()
         t0 = time.perf_counter()
         ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.active = True
         ee0.record()
         for _ in range(e2e_steps):
             e2e_step()
         ee1.record()
         barrier()
+        if sampler:
+            sampler.active = False
         wall = (time.perf_counter() - t0) * 1e3
         ems = max(ee0.elapsed_time(ee1), 0.0)
         ems = max(ems, wall) if ems == 0 else ems
@@ -400,6 +413,8 @@ def main():
                "d2h_bytes_per_step": int(gn.nbytes), "ms_per_step": ems / e2e_steps, "steps": e2e_steps,
                "what": "pinned host X,dA -> HBM, fwd+grad, [dW||db] -> pinned host, every step"}
 
+    # the sampler ran through the timed region, the TF32 side measurement and the e2e region: all of it is load
+    clocks = sampler.stop() if sampler else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
