@@ -1,4 +1,5 @@
-// Instantiations, TMA tensor-map construction and launch logic for the tcgen05 GEMM (gemm_sm100.cuh).
+// TMA tensor-map construction, tiling / split-K decisions and dispatch for the tcgen05 GEMM (gemm_sm100.cuh); the kernel
+// instantiations live in gemm_sm100_inst_*.cu.
 #include "gemm_sm100.h"
 
 #include <cuda.h>
@@ -48,58 +49,21 @@ bool make_map(CUtensorMap* m, int dtype, const void* ptr, long long inner, long 
     return r == CUDA_SUCCESS;
 }
 
-template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
-cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-    using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
-    auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES, CG>;
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    if constexpr (CG == 1) {
-        kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], p);
-        return cudaGetLastError();
-    } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::NUM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], p);
-    }
-}
+}  // namespace
 
-template <typename T, int MA, int MB, int CG>
-cudaError_t launch_cg(int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-    // stage bytes: 1-pass (128 + bn/CG) * 128, 3-pass twice that; stage counts fill the 227 KiB left after the epilogue staging
-    if constexpr (sizeof(T) == 4) {
-        if (passes == 3) {
-            if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 4 : 3, 3, CG>(tm, p, grid, st);
-            return launch_one<T, MA, MB, 256, CG == 2 ? 3 : 2, 3, CG>(tm, p, grid, st);
-        }
-        // fp32 1-pass: one stage fewer than fits, so that each epilogue warp gets separate aux and output staging blocks
-        if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 6 : 5, 1, CG>(tm, p, grid, st);
-        return launch_one<T, MA, MB, 256, CG == 2 ? 5 : 3, 1, CG>(tm, p, grid, st);
-    }
-    if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 8 : 6, 1, CG>(tm, p, grid, st);
-    return launch_one<T, MA, MB, 256, CG == 2 ? 6 : 4, 1, CG>(tm, p, grid, st);
-}
+// defined in gemm_sm100_inst_{kk,kmn,mnk,mnmn}.cu
+cudaError_t gemm_launch_kk(int dtype, int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st);
+cudaError_t gemm_launch_kmn(int dtype, int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st);
+cudaError_t gemm_launch_mnk(int dtype, int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st);
+cudaError_t gemm_launch_mnmn(int dtype, int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st);
 
-template <typename T, int MA, int MB>
-cudaError_t launch_major(int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-    if (cg == 2) return launch_cg<T, MA, MB, 2>(bn, passes, tm, p, grid, st);
-    return launch_cg<T, MA, MB, 1>(bn, passes, tm, p, grid, st);
-}
+namespace {
 
-template <typename T>
-cudaError_t launch_dtype(int cg, int ma, int mb, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-    if (ma == MAJOR_K && mb == MAJOR_K) return launch_major<T, MAJOR_K, MAJOR_K>(cg, bn, passes, tm, p, grid, st);
-    if (ma == MAJOR_K && mb == MAJOR_MN) return launch_major<T, MAJOR_K, MAJOR_MN>(cg, bn, passes, tm, p, grid, st);
-    if (ma == MAJOR_MN && mb == MAJOR_K) return launch_major<T, MAJOR_MN, MAJOR_K>(cg, bn, passes, tm, p, grid, st);
-    return launch_major<T, MAJOR_MN, MAJOR_MN>(cg, bn, passes, tm, p, grid, st);
+cudaError_t launch_any(int dtype, int cg, int ma, int mb, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+    if (ma == MAJOR_K && mb == MAJOR_K) return gemm_launch_kk(dtype, cg, bn, passes, tm, p, grid, st);
+    if (ma == MAJOR_K && mb == MAJOR_MN) return gemm_launch_kmn(dtype, cg, bn, passes, tm, p, grid, st);
+    if (ma == MAJOR_MN && mb == MAJOR_K) return gemm_launch_mnk(dtype, cg, bn, passes, tm, p, grid, st);
+    return gemm_launch_mnmn(dtype, cg, bn, passes, tm, p, grid, st);
 }
 
 }  // namespace
@@ -193,8 +157,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     const int total = tiles * p.split_k;
     const int grid = (total < ctas ? total : ctas) * cg;
     cudaError_t e;
-    if (c.dtype == 1) e = launch_dtype<__nv_bfloat16>(cg, c.major_a, c.major_b, bn, 1, tm, p, grid, stream);
-    else e = launch_dtype<float>(cg, c.major_a, c.major_b, bn, c.passes == 3 ? 3 : 1, tm, p, grid, stream);
+    e = launch_any(c.dtype, cg, c.major_a, c.major_b, bn, c.passes == 3 ? 3 : 1, tm, p, grid, stream);
     if (e != cudaSuccess) {
         if (err && errlen) snprintf(err, errlen, "gemm launch: %s", cudaGetErrorString(e));
         return (int)e;

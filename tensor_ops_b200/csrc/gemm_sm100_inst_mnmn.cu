@@ -1,0 +1,6 @@
+// tcgen05 GEMM kernel variants with A MAJOR_MN, B MAJOR_MN (see gemm_sm100_launch.cuh)
+#include "gemm_sm100_launch.cuh"
+
+namespace tops {
+TOPS_DEFINE_GEMM_VARIANT(gemm_launch_mnmn, MAJOR_MN, MAJOR_MN)
+}  // namespace tops

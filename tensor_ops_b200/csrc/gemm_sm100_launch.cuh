@@ -1,0 +1,64 @@
+// Kernel instantiation + launch templates of the tcgen05 GEMM, shared by the per-layout translation units
+// (gemm_sm100_inst_*.cu): the 64 kernel variants are split over four files by operand layout so that they compile in parallel.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "gemm_sm100.cuh"
+
+namespace tops {
+
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
+cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+    using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
+    auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES, CG>;
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if constexpr (CG == 1) {
+        kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], p);
+        return cudaGetLastError();
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::NUM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], p);
+    }
+}
+
+template <typename T, int MA, int MB, int CG>
+cudaError_t launch_cg(int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+    // stage bytes: 1-pass (128 + bn/CG) * 128, 3-pass twice that; stage counts fill the 227 KiB left after the epilogue staging
+    if constexpr (sizeof(T) == 4) {
+        if (passes == 3) {
+            if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 4 : 3, 3, CG>(tm, p, grid, st);
+            return launch_one<T, MA, MB, 256, CG == 2 ? 3 : 2, 3, CG>(tm, p, grid, st);
+        }
+        // fp32 1-pass: one stage fewer than fits, so that each epilogue warp gets separate aux and output staging blocks
+        if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 6 : 5, 1, CG>(tm, p, grid, st);
+        return launch_one<T, MA, MB, 256, CG == 2 ? 5 : 3, 1, CG>(tm, p, grid, st);
+    }
+    if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 8 : 6, 1, CG>(tm, p, grid, st);
+    return launch_one<T, MA, MB, 256, CG == 2 ? 6 : 4, 1, CG>(tm, p, grid, st);
+}
+
+template <typename T, int MA, int MB>
+cudaError_t launch_major(int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+    if (cg == 2) return launch_cg<T, MA, MB, 2>(bn, passes, tm, p, grid, st);
+    return launch_cg<T, MA, MB, 1>(bn, passes, tm, p, grid, st);
+}
+
+// one entry per (A layout, B layout); dtype 0 = fp32 operands, 1 = bf16
+#define TOPS_DEFINE_GEMM_VARIANT(NAME, MA, MB)                                                                                          \
+    cudaError_t NAME(int dtype, int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {    \
+        if (dtype == 1) return launch_major<__nv_bfloat16, MA, MB>(cg, bn, 1, tm, p, grid, st);                                        \
+        return launch_major<float, MA, MB>(cg, bn, passes, tm, p, grid, st);                                                           \
+    }
+
+}  // namespace tops
