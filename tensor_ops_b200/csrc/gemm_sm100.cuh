@@ -10,20 +10,24 @@
 //   dW = dZ^T X        (A = dZ MN-major, B = X  MN-major, split-K)
 // run on the tensor cores without any transposed copy in HBM.
 //
-// Roles (one CTA per SM, persistent over work items):
+// One CTA per SM, persistent over work items (output tile x split-K partition).  By default two CTAs form a cluster and work as a
+// CTA PAIR on a 256-row tile (CG = 2, tcgen05 cta_group::2): each stages its 128 rows of A and half of the B tile, the leader issues
+// the MMAs for both, accumulators stay in each CTA's own TMEM.  CG = 1 is the same code with one CTA per 128-row tile.
+//
+// Roles (384 threads 1-pass, 512 threads 3-pass; registers rebalanced between warpgroups with setmaxnreg):
 //   warp 0      TMA producer      global -> 128B-swizzled smem ring (mbarrier full[])
-//   warp 1      MMA issuer        one thread issues tcgen05.mma into TMEM, commits to empty[] / tmem_full[]
+//   warp 1      MMA issuer        one thread (leader CTA) issues tcgen05.mma into TMEM, commits to empty[] / tmem_full[] (multicast for CG = 2)
 //   warp 2      TMEM allocator
-//   1-pass (TF32 / bf16 throughput modes), 256 threads:
-//     warps 4-7   epilogue        tcgen05.ld -> registers -> fused bias / logistic / VJP math -> global; the whole K range
-//                                 of a work item accumulates in one TMEM buffer, double-buffered across work items
-//   3-pass (3xTF32, the fp32-grade parity mode), 512 threads, registers rebalanced with setmaxnreg:
-//     warps 4-11  epilogue        The tensor core's accumulator add TRUNCATES (measured: error grows linearly, ~2e-8 relative
-//                                 per MMA; 8e-6 after K = 1024), so TMEM only ever holds a CHUNK of `chunk_kb` k-blocks.  Each
-//                                 chunk is drained with tcgen05.ld and added, round-to-nearest fp32, into register accumulators
-//                                 (128 per thread: warp w owns TMEM lane quarter w%4 and column half (w-4)/4) while the MMA
-//                                 warp fills the other TMEM buffer; the fused epilogue math runs from the registers.
-//     warps 12-15 splitter        lo = x - trunc_tf32(x) into a second tile (ready[]); the raw tile serves as hi
+//   warp 3      relay (CG = 2, 1-pass): forwards "my stage has landed" to the leader's ready[] barrier
+//   warps 4-11  epilogue          2 warps per TMEM lane quarter, each owning half of the tile's columns: tcgen05.ld -> registers -> fused
+//                                 bias / logistic / VJP / loss math -> 32x32 staging block in smem -> coalesced 16-byte global stores;
+//                                 the aux operand arrives by TMA into a staging block; column sums (db) are taken from the staged block.
+//                                 1-pass: the whole K range of a work item accumulates in one TMEM buffer, double-buffered across work items.
+//                                 3-pass: the tensor core's accumulator add TRUNCATES (measured: error grows linearly, ~2.7e-8 relative per
+//                                 MMA; 8e-6 after K = 1024), so TMEM only ever holds a CHUNK of `chunk_kb` k-blocks; each chunk is drained
+//                                 and added, round-to-nearest fp32, into 128 register accumulators per thread while the MMA warp fills the
+//                                 other TMEM buffer; the fused epilogue math then runs from the registers.
+//   warps 12-15 splitter (3-pass) lo = x - trunc_tf32(x) into a second tile (ready[]); the raw tile serves as hi
 #pragma once
 
 #include <cuda_bf16.h>
@@ -66,7 +70,7 @@ struct GemmParams {
     int* tile_counters;       // [num_tiles * CG * 8] zeroed by the caller
     int io_bf16;              // out0/out1/aux0 are bf16 (bf16 pipelines); 0 = fp32
     int vec_ok;               // 16-byte vector access legal for out0/out1/aux0
-    int tma_epi;              // epilogue I/O goes through smem staging + TMA (tensor maps tmO0/tmO1/tmAux are valid)
+    int tma_epi;              // staged epilogue: outputs via smem staging + coalesced stores, aux operand by TMA (tmAux valid if needed)
     unsigned int* watchdog;   // mapped host memory, 2 words
 };
 
@@ -318,19 +322,18 @@ __device__ __forceinline__ void stage_colsum(uint32_t buf, int lane, int col, in
     constexpr int ROWB = W * (int)sizeof(IO);
     constexpr int EPC = 16 / (int)sizeof(IO);          // elements per 16-byte chunk
     static_assert(W == 32, "one column per lane");
-    float s = 0.f;
-    constexpr int NSW = ROWB == 128 ? 8 : 4;           // distinct swizzle patterns; rows r and r + period share one
+    float part[4] = {0.f, 0.f, 0.f, 0.f};            // independent partial sums: no 32-long dependent FADD chain
     constexpr int PERIOD = 8;                          // stage_off(r + 8, j) == stage_off(r, j) + 8 * ROWB for both layouts
 #pragma unroll
     for (int k = 0; k < PERIOD; ++k) {
         const uint32_t a = buf + stage_off<ROWB>(k, lane / EPC) + (lane % EPC) * (int)sizeof(IO);
 #pragma unroll
         for (int m = 0; m < 32 / PERIOD; ++m) {
-            if constexpr (sizeof(IO) == 2) s += __uint_as_float(static_cast<uint32_t>(ptx::lds16(a + m * PERIOD * ROWB)) << 16);
-            else s += ptx::lds32f(a + m * PERIOD * ROWB);
+            if constexpr (sizeof(IO) == 2) part[m] += __uint_as_float(static_cast<uint32_t>(ptx::lds16(a + m * PERIOD * ROWB)) << 16);
+            else part[m] += ptx::lds32f(a + m * PERIOD * ROWB);
         }
     }
-    (void)NSW;
+    const float s = (part[0] + part[1]) + (part[2] + part[3]);
     if (col + lane < N) atomicAdd(colsum + col + lane, s);
 }
 
@@ -350,11 +353,14 @@ __device__ __forceinline__ void stage_store_global(uint32_t buf, int lane, void*
         // rows rl + k*RPI.  128-byte rows: RPI = 4, the swizzle (r & 7) alternates between two values; 64-byte rows: RPI = 8, constant
         const uint32_t s0 = buf + stage_off<ROWB>(rl, j);
         const uint32_t s1 = buf + stage_off<ROWB>(rl + RPI, j);
+        uint4 u[CPR];                              // all shared loads first, then all global stores: the LDS latency is paid once
 #pragma unroll
         for (int k = 0; k < CPR; ++k) {
             const uint32_t a = (ROWB == 128) ? ((k & 1) ? s1 : s0) + (k >> 1) * (2 * RPI * ROWB) : s0 + k * (RPI * ROWB);
-            *reinterpret_cast<uint4*>(g0 + (long long)k * RPI * ld) = ptx::lds128(a);
+            u[k] = ptx::lds128(a);
         }
+#pragma unroll
+        for (int k = 0; k < CPR; ++k) *reinterpret_cast<uint4*>(g0 + (long long)k * RPI * ld) = u[k];
         return;
     }
     if (c >= N) return;
