@@ -74,7 +74,9 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
         return code;
     };
     if (c.M <= 0 || c.N <= 0 || c.K <= 0) return fail(-1, "gemm: empty problem");
-    if (c.passes == 3 && c.dtype != 0) return fail(-1, "gemm: 3-pass split needs fp32 operands");
+    if (c.passes >= 2 && c.dtype != 0) return fail(-1, "gemm: the split modes need fp32 operands");
+    int passes = c.passes >= 2 ? c.passes : 1;
+    if (passes == 2 && !(c.major_a == MAJOR_K && c.major_b == MAJOR_K)) passes = 3;   // bf16-correction mode re-tiles K-major operands only
     const int es = c.dtype == 1 ? 2 : 4;
     const int kb_elems = 128 / es;
     int bn = c.block_n;
@@ -157,7 +159,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     const int total = tiles * p.split_k;
     const int grid = (total < ctas ? total : ctas) * cg;
     cudaError_t e;
-    e = launch_any(c.dtype, cg, c.major_a, c.major_b, bn, c.passes == 3 ? 3 : 1, tm, p, grid, stream);
+    e = launch_any(c.dtype, cg, c.major_a, c.major_b, bn, passes, tm, p, grid, stream);
     if (e != cudaSuccess) {
         if (err && errlen) snprintf(err, errlen, "gemm launch: %s", cudaGetErrorString(e));
         return (int)e;

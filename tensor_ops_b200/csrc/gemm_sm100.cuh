@@ -84,8 +84,10 @@ struct GemmCfg {
     static constexpr int B_BYTES = (BN / CG) * 128;   // a CTA pair (CG = 2) splits the B tile: each CTA stages N/2 rows
     static_assert(CG == 1 || CG == 2, "CTA group size");
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGE_BYTES = RAW_BYTES * (PASSES == 3 ? 2 : 1);
-    static constexpr int NUM_THREADS = PASSES == 3 ? 512 : 384;
+    // split modes keep a second set of tiles per stage: PASSES == 3 the fp32 lo tiles (RAW_BYTES); PASSES == 2 four bf16 tiles
+    // (bf16(A), bf16(A_lo), bf16(B), bf16(B_lo)), half the bytes each — RAW_BYTES in total as well
+    static constexpr int STAGE_BYTES = RAW_BYTES * (PASSES >= 2 ? 2 : 1);
+    static constexpr int NUM_THREADS = PASSES >= 2 ? 512 : 384;
     static constexpr int EPI_THREADS = 256;                 // 8 epilogue warps: 2 per TMEM lane quarter, each owning half of the tile's columns
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 512;
@@ -102,7 +104,8 @@ struct GemmCfg {
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + EPI_BYTES + 1024 /*alignment slack*/;
     static_assert(BAR_BYTES <= 1024 && (3 * STAGES + 4 + EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier area");
-    static_assert(PASSES == 1 || (PASSES == 3 && sizeof(T) == 4), "3-pass split is an fp32 technique");
+    static_assert(PASSES == 1 || (PASSES >= 2 && PASSES <= 3 && sizeof(T) == 4), "the hi/lo split modes are fp32 techniques");
+    static_assert(PASSES != 2 || (MA == 0 && MB == 0), "the bf16-correction mode re-tiles the operands in software: K-major only");
     static_assert(BN == 128 || BN == 256, "BN");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -466,7 +469,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const GemmParams p) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
     constexpr bool kBF16 = sizeof(T) == 2;
-    constexpr bool kChunked = PASSES == 3;   // TMEM holds one chunk; the running sum lives in epilogue registers
+    constexpr bool kChunked = PASSES >= 2;   // TMEM holds one chunk; the running sum lives in epilogue registers
     constexpr int BM = Cfg::BM;
     constexpr int KB = Cfg::KB_ELEMS;
     constexpr int kSplitWarp0 = 12;          // first splitter warp (3-pass layout)
@@ -504,7 +507,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::mbar_init(&empty_bar[s], 1);
             // ready: CG = 1: the 128 splitter threads (3-pass).  CG = 2: splitter threads of both CTAs (3-pass) or the two
             // relay threads that forward "my TMA data has landed" to the leader (1-pass)
-            ptx::mbar_init(&ready_bar[s], CG == 1 ? 128 : (PASSES == 3 ? 256 : 2));
+            ptx::mbar_init(&ready_bar[s], CG == 1 ? 128 : (PASSES >= 2 ? 256 : 2));
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
@@ -593,6 +596,35 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         ptx::tcgen05_fence_after();
                         const uint32_t sa = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
                         const uint32_t sb = sa + Cfg::A_BYTES;
+                        if constexpr (PASSES == 2) {
+                            // hi*hi in TF32 from the raw tiles (the hardware truncates), then the two first-order corrections
+                            //   bf16(A_lo) * bf16(B)   and   bf16(A) * bf16(B_lo)
+                            // as bf16 MMAs: K = 16 per instruction, so each correction pass costs half a TF32 pass.  Their rounding
+                            // error (2^-9 on a term that is 2^-11 of the product) is ~2^-20 per product, unbiased.
+                            if constexpr (CG == 1) { ptx::mbar_wait(&ready_bar[s], ph, wd, 0x340 + s); ptx::tcgen05_fence_after(); }
+                            constexpr uint32_t idesc16 = ptx::make_idesc(1u, 0, 0, BM * CG, BN);
+                            const uint32_t a16 = sa + Cfg::RAW_BYTES, alo16 = a16 + Cfg::A_BYTES / 2;
+                            const uint32_t b16 = alo16 + Cfg::A_BYTES / 2, blo16 = b16 + Cfg::B_BYTES / 2;
+#pragma unroll
+                            for (int j = 0; j < Cfg::KSTEPS; ++j) {
+                                const uint64_t ad = ptx::make_smem_desc_sw128(sa + j * 32u, 16u, 1024u, 2u);
+                                const uint64_t bd = ptx::make_smem_desc_sw128(sb + j * 32u, 16u, 1024u, 2u);
+                                if constexpr (CG == 2) ptx::umma_tf32_2cta(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                else ptx::umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+#pragma unroll
+                            for (int pass = 1; pass <= 2; ++pass) {
+                                const uint32_t pa = pass == 1 ? alo16 : a16, pb = pass == 1 ? b16 : blo16;
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {   // 32 K-elements = 2 x (K = 16): 32 bytes per step inside the 64-byte rows
+                                    const uint64_t ad = ptx::make_smem_desc_sw128(pa + j * 32u, 16u, 512u, 4u);   // SWIZZLE_64B, 8-row groups of 512 B
+                                    const uint64_t bd = ptx::make_smem_desc_sw128(pb + j * 32u, 16u, 512u, 4u);
+                                    if constexpr (CG == 2) ptx::umma_f16_2cta(d_tmem, ad, bd, idesc16, 1u);
+                                    else ptx::umma_f16(d_tmem, ad, bd, idesc16, 1u);
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int pass = 0; pass < PASSES; ++pass) {
                             // pass 0: A_hi*B_hi   pass 1: A_lo*B_hi   pass 2: A_hi*B_lo
@@ -617,6 +649,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 }
                                 first = 0;
                             }
+                        }
                         }
                         if constexpr (CG == 2) ptx::umma_commit_2cta(&empty_bar[s], 0x3);   // frees the stage in both CTAs
                         else ptx::umma_commit(&empty_bar[s]);
@@ -781,6 +814,37 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ptx::mbar_wait(&full_bar[s], ph, wd, 0x500 + s);
                 const uint32_t hi = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
                 const uint32_t lo = hi + Cfg::RAW_BYTES;
+                if constexpr (PASSES == 2) {
+                    // K-major raw tiles: row r = 32 fp32 = 128 bytes, SWIZZLE_128B (16-byte chunk c of row r at (c ^ (r & 7))).
+                    // One task = 8 consecutive K-elements of one row (two raw chunks) -> one 16-byte chunk of the bf16 tile and one of
+                    // the bf16 lo tile; bf16 rows are 64 bytes, SWIZZLE_64B (chunk c2 of row r at (c2 ^ ((r >> 1) & 3))).
+                    constexpr int ROWS = BM + BN / CG;                     // A rows then B rows, each with its own pair of bf16 tiles
+#pragma unroll 2
+                    for (int i = t; i < ROWS * 4; i += 128) {
+                        const int r = i >> 2, c2 = i & 3;                  // row (over A then B), bf16 chunk
+                        const uint32_t raw_row = hi + r * 128;
+                        const uint4 x0 = ptx::lds128(raw_row + (((2 * c2) ^ (r & 7)) << 4));
+                        const uint4 x1 = ptx::lds128(raw_row + (((2 * c2 + 1) ^ (r & 7)) << 4));
+                        const float f[8] = {__uint_as_float(x0.x), __uint_as_float(x0.y), __uint_as_float(x0.z), __uint_as_float(x0.w),
+                                            __uint_as_float(x1.x), __uint_as_float(x1.y), __uint_as_float(x1.z), __uint_as_float(x1.w)};
+                        uint4 v16, l16;
+                        __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v16);
+                        __nv_bfloat162* hl = reinterpret_cast<__nv_bfloat162*>(&l16);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a0 = f[2 * e], a1 = f[2 * e + 1];
+                            hv[e] = __floats2bfloat162_rn(a0, a1);
+                            hl[e] = __floats2bfloat162_rn(a0 - __uint_as_float(__float_as_uint(a0) & 0xffffe000u),
+                                                          a1 - __uint_as_float(__float_as_uint(a1) & 0xffffe000u));
+                        }
+                        // A rows -> (A16, Alo16) tiles, B rows -> (B16, Blo16) tiles; each tile: rows * 64 bytes
+                        const bool isA = r < BM;
+                        const int rr = isA ? r : r - BM;
+                        const uint32_t t16 = lo + (isA ? 0 : Cfg::A_BYTES) + rr * 64 + ((c2 ^ ((rr >> 1) & 3)) << 4);
+                        ptx::sts128(t16, v16);
+                        ptx::sts128(t16 + (isA ? Cfg::A_BYTES : Cfg::B_BYTES) / 2, l16);
+                    }
+                } else {
 #pragma unroll 4
                 for (int i = t; i < Cfg::RAW_BYTES / 16; i += 128) {
                     // kind::tf32 TRUNCATES fp32 operands (measured: tools/gemm_probe, ref_mode=1), so the raw tile already
@@ -792,6 +856,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(x.z & 0xffffe000u));
                     l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(x.w & 0xffffe000u));
                     ptx::sts128(lo + i * 16, l);
+                }
                 }
                 ptx::fence_proxy_async_smem();
                 if constexpr (CG == 2) ptx::mbar_arrive_cluster(ready0 + s * 8);
