@@ -47,9 +47,11 @@ typedef enum { TOPS_F32 = 0, TOPS_BF16 = 1 } tops_dtype;
 
 /* How fp32 GEMM-class work (gemm, gmul with |os|>=1 on matrices, the fused ffLayer paths) uses the tensor cores. */
 typedef enum {
-    TOPS_PREC_TF32X3 = 0,  /* default: 3-pass hi/lo TF32 split on tcgen05, fp32-grade accuracy (~1e-6 rel)  */
+    TOPS_PREC_TF32X3 = 0,  /* 3-pass hi/lo TF32 split on tcgen05 (hi*hi + lo*hi + hi*lo), fp32-grade accuracy (~1.5e-6 rel) */
     TOPS_PREC_TF32 = 1,    /* single TF32 pass on tcgen05 (~1e-3 rel), the throughput mode                   */
-    TOPS_PREC_FP32_SIMT = 2 /* CUDA-core FFMA kernel (exact fp32 products); also what un-TMA-able strides use */
+    TOPS_PREC_FP32_SIMT = 2, /* CUDA-core FFMA kernel (exact fp32 products); also what un-TMA-able strides use */
+    TOPS_PREC_TF32_BF16X2 = 3 /* default: hi*hi in TF32 + the two first-order corrections bf16(lo)*bf16(x) as bf16 MMAs (half the cost of a
+                                 TF32 pass each): fp32-grade accuracy (~1.4e-6 rel) at 2 tensor-core passes instead of 3 */
 } tops_precision;
 
 typedef enum { TOPS_ACT_ID = 0, TOPS_ACT_LOGISTIC = 1, TOPS_ACT_SOFTMAX = 2 } tops_act;

@@ -13,10 +13,10 @@ Layout
 """
 from . import _lib
 from ._lib import (ACT_ID, ACT_LOGISTIC, ACT_SOFTMAX, BF16, F32, LOSS_CROSS_ENTROPY, LOSS_SQUARED_ERROR,
-                   PREC_FP32_SIMT, PREC_TF32, PREC_TF32X3, TopsError)
+                   PREC_FP32_SIMT, PREC_TF32, PREC_TF32X3, PREC_TF32_BF16X2, TopsError)
 from .tensor import Context, CuTensor, default_context
 from . import expr, top, nn, batched
 
 __all__ = ["Context", "CuTensor", "default_context", "expr", "top", "nn", "batched", "TopsError",
-           "F32", "BF16", "PREC_TF32X3", "PREC_TF32", "PREC_FP32_SIMT", "ACT_ID", "ACT_LOGISTIC", "ACT_SOFTMAX",
+           "F32", "BF16", "PREC_TF32X3", "PREC_TF32", "PREC_FP32_SIMT", "PREC_TF32_BF16X2", "ACT_ID", "ACT_LOGISTIC", "ACT_SOFTMAX",
            "LOSS_SQUARED_ERROR", "LOSS_CROSS_ENTROPY"]

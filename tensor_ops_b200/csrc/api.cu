@@ -25,7 +25,7 @@ struct tops_ctx {
     cudaStream_t stream = nullptr;
     std::recursive_mutex mu;
     std::string last_error;
-    int precision = TOPS_PREC_TF32X3;
+    int precision = TOPS_PREC_TF32_BF16X2;
     int fused_chunk_kb = 8;
     int64_t launches = 0;
     unsigned int* wd_host = nullptr;
@@ -197,7 +197,7 @@ int run_gemm(tops_ctx* ctx, GemmCall c) {
     }
     const bool want_umma = c.dtype == 1 || ctx->precision != TOPS_PREC_FP32_SIMT;
     if (want_umma) {
-        c.passes = (c.dtype == 0 && ctx->precision == TOPS_PREC_TF32X3) ? 3 : 1;
+        c.passes = c.dtype != 0 ? 1 : ctx->precision == TOPS_PREC_TF32X3 ? 3 : ctx->precision == TOPS_PREC_TF32_BF16X2 ? 2 : 1;
         char err[256];
         int r = gemm_umma_launch(c, ctx->stream, ctx->wd_dev, ctx->num_sms, err, sizeof err);
         if (r == 0) { ++ctx->launches; return TOPS_OK; }
@@ -287,7 +287,7 @@ extern "C" int tops_sync(tops_ctx* ctx) {
 extern "C" int tops_set_stream(tops_ctx* ctx, void* s) { CHECK_CTX(ctx); LOCK(ctx); ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return TOPS_OK; }
 extern "C" int tops_set_precision(tops_ctx* ctx, int p) {
     CHECK_CTX(ctx); LOCK(ctx);
-    if (p < 0 || p > 2) return set_err(ctx, TOPS_ERR_INVALID, "unknown precision %d", p);
+    if (p < 0 || p > 3) return set_err(ctx, TOPS_ERR_INVALID, "unknown precision %d", p);
     ctx->precision = p;
     return TOPS_OK;
 }

@@ -76,7 +76,6 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     if (c.M <= 0 || c.N <= 0 || c.K <= 0) return fail(-1, "gemm: empty problem");
     if (c.passes >= 2 && c.dtype != 0) return fail(-1, "gemm: the split modes need fp32 operands");
     int passes = c.passes >= 2 ? c.passes : 1;
-    if (passes == 2 && !(c.major_a == MAJOR_K && c.major_b == MAJOR_K)) passes = 3;   // bf16-correction mode re-tiles K-major operands only
     const int es = c.dtype == 1 ? 2 : 4;
     const int kb_elems = 128 / es;
     int bn = c.block_n;

@@ -32,6 +32,8 @@
 
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "umma.cuh"
 
 namespace tops {
@@ -105,7 +107,6 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + EPI_BYTES + 1024 /*alignment slack*/;
     static_assert(BAR_BYTES <= 1024 && (3 * STAGES + 4 + EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier area");
     static_assert(PASSES == 1 || (PASSES >= 2 && PASSES <= 3 && sizeof(T) == 4), "the hi/lo split modes are fp32 techniques");
-    static_assert(PASSES != 2 || (MA == 0 && MB == 0), "the bf16-correction mode re-tiles the operands in software: K-major only");
     static_assert(BN == 128 || BN == 256, "BN");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -463,6 +464,32 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, const CUtensorMap
     }
 }
 
+// 8 fp32 values -> 8 x bf16(x) and 8 x bf16(x - trunc_tf32(x))   (operands of the two bf16 correction passes)
+__device__ __forceinline__ void split8_bf16(const uint4& x0, const uint4& x1, uint4& v16, uint4& l16) {
+    const float f[8] = {__uint_as_float(x0.x), __uint_as_float(x0.y), __uint_as_float(x0.z), __uint_as_float(x0.w),
+                        __uint_as_float(x1.x), __uint_as_float(x1.y), __uint_as_float(x1.z), __uint_as_float(x1.w)};
+    __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v16);
+    __nv_bfloat162* hl = reinterpret_cast<__nv_bfloat162*>(&l16);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float a0 = f[2 * e], a1 = f[2 * e + 1];
+        hv[e] = __floats2bfloat162_rn(a0, a1);
+        hl[e] = __floats2bfloat162_rn(a0 - __uint_as_float(__float_as_uint(a0) & 0xffffe000u), a1 - __uint_as_float(__float_as_uint(a1) & 0xffffe000u));
+    }
+}
+
+__device__ __forceinline__ void split4_bf16(const uint4& x, uint2& v8, uint2& l8) {
+    const float f[4] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)};
+    __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v8);
+    __nv_bfloat162* hl = reinterpret_cast<__nv_bfloat162*>(&l8);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float a0 = f[2 * e], a1 = f[2 * e + 1];
+        hv[e] = __floats2bfloat162_rn(a0, a1);
+        hl[e] = __floats2bfloat162_rn(a0 - __uint_as_float(__float_as_uint(a0) & 0xffffe000u), a1 - __uint_as_float(__float_as_uint(a1) & 0xffffe000u));
+    }
+}
+
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
 __global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>::NUM_THREADS), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAux,
@@ -602,24 +629,31 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             // as bf16 MMAs: K = 16 per instruction, so each correction pass costs half a TF32 pass.  Their rounding
                             // error (2^-9 on a term that is 2^-11 of the product) is ~2^-20 per product, unbiased.
                             if constexpr (CG == 1) { ptx::mbar_wait(&ready_bar[s], ph, wd, 0x340 + s); ptx::tcgen05_fence_after(); }
-                            constexpr uint32_t idesc16 = ptx::make_idesc(1u, 0, 0, BM * CG, BN);
+                            constexpr uint32_t idesc16 = ptx::make_idesc(1u, MA == MAJOR_MN, MB == MAJOR_MN, BM * CG, BN);
                             const uint32_t a16 = sa + Cfg::RAW_BYTES, alo16 = a16 + Cfg::A_BYTES / 2;
                             const uint32_t b16 = alo16 + Cfg::A_BYTES / 2, blo16 = b16 + Cfg::B_BYTES / 2;
 #pragma unroll
                             for (int j = 0; j < Cfg::KSTEPS; ++j) {
-                                const uint64_t ad = ptx::make_smem_desc_sw128(sa + j * 32u, 16u, 1024u, 2u);
-                                const uint64_t bd = ptx::make_smem_desc_sw128(sb + j * 32u, 16u, 1024u, 2u);
+                                const uint64_t ad = ptx::make_smem_desc_sw128(sa + j * a_step, a_lbo, a_sbo, a_lt);
+                                const uint64_t bd = ptx::make_smem_desc_sw128(sb + j * b_step, b_lbo, b_sbo, b_lt);
                                 if constexpr (CG == 2) ptx::umma_tf32_2cta(d_tmem, ad, bd, idesc, first ? 0u : 1u);
                                 else ptx::umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
                                 first = 0;
                             }
+                            // bf16 tiles written by the splitter.  K-major: rows = MN index, 64 bytes each, SWIZZLE_64B (8-row groups of 512 B),
+                            // 32 bytes per K = 16 step.  MN-major: 64-element MN groups of [32 k-rows x 128 B], SWIZZLE_128B (LBO = 4096 between
+                            // groups, SBO = 1024 between 8-row atoms), 16 k-rows = 2048 bytes per step.
+                            constexpr uint32_t a16_lt = MA == MAJOR_K ? 4u : 2u, b16_lt = MB == MAJOR_K ? 4u : 2u;
+                            constexpr uint32_t a16_lbo = MA == MAJOR_K ? 16u : 4096u, b16_lbo = MB == MAJOR_K ? 16u : 4096u;
+                            constexpr uint32_t a16_sbo = MA == MAJOR_K ? 512u : 1024u, b16_sbo = MB == MAJOR_K ? 512u : 1024u;
+                            constexpr uint32_t a16_step = MA == MAJOR_K ? 32u : 2048u, b16_step = MB == MAJOR_K ? 32u : 2048u;
 #pragma unroll
                             for (int pass = 1; pass <= 2; ++pass) {
                                 const uint32_t pa = pass == 1 ? alo16 : a16, pb = pass == 1 ? b16 : blo16;
 #pragma unroll
-                                for (int j = 0; j < 2; ++j) {   // 32 K-elements = 2 x (K = 16): 32 bytes per step inside the 64-byte rows
-                                    const uint64_t ad = ptx::make_smem_desc_sw128(pa + j * 32u, 16u, 512u, 4u);   // SWIZZLE_64B, 8-row groups of 512 B
-                                    const uint64_t bd = ptx::make_smem_desc_sw128(pb + j * 32u, 16u, 512u, 4u);
+                                for (int j = 0; j < 2; ++j) {   // 32 K-elements = 2 x (K = 16)
+                                    const uint64_t ad = ptx::make_smem_desc_sw128(pa + j * a16_step, a16_lbo, a16_sbo, a16_lt);
+                                    const uint64_t bd = ptx::make_smem_desc_sw128(pb + j * b16_step, b16_lbo, b16_sbo, b16_lt);
                                     if constexpr (CG == 2) ptx::umma_f16_2cta(d_tmem, ad, bd, idesc16, 1u);
                                     else ptx::umma_f16(d_tmem, ad, bd, idesc16, 1u);
                                 }
@@ -815,35 +849,45 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t hi = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
                 const uint32_t lo = hi + Cfg::RAW_BYTES;
                 if constexpr (PASSES == 2) {
-                    // K-major raw tiles: row r = 32 fp32 = 128 bytes, SWIZZLE_128B (16-byte chunk c of row r at (c ^ (r & 7))).
-                    // One task = 8 consecutive K-elements of one row (two raw chunks) -> one 16-byte chunk of the bf16 tile and one of
-                    // the bf16 lo tile; bf16 rows are 64 bytes, SWIZZLE_64B (chunk c2 of row r at (c2 ^ ((r >> 1) & 3))).
-                    constexpr int ROWS = BM + BN / CG;                     // A rows then B rows, each with its own pair of bf16 tiles
+                    // One task = 8 consecutive elements along the contiguous dimension of a raw fp32 tile (32 bytes) -> one 16-byte chunk
+                    // of the operand's bf16 tile and one of its bf16 lo tile.
+                    //  K-major raw: row r (MN index) = 32 K-elements = 128 bytes, SWIZZLE_128B: 16-byte chunk c at (c ^ (r & 7)).
+                    //          bf16: rows of 64 bytes, SWIZZLE_64B: chunk c2 at (c2 ^ ((r >> 1) & 3)).
+                    //  MN-major raw: boxes of [32 k-rows x 32 MN-elements (128 bytes)], SWIZZLE_128B_ATOM_32B: 32-byte unit u of row k at
+                    //          (u ^ (k & 3)).   bf16: 64-element MN groups of [32 k-rows x 128 bytes], SWIZZLE_128B: chunk c at (c ^ (k & 7)).
+                    // One task = 8 consecutive elements along the contiguous dimension of a raw tile (two 16-byte loads) -> one 16-byte
+                    // chunk of the operand's bf16 tile and one of its bf16 lo tile.  A and B are handled by two loops so that every
+                    // size / layout is a compile-time constant.
+                    auto split_operand = [&](auto kmajor_tag, auto mn_tag, uint32_t raw, uint32_t t16) {
+                        constexpr bool kmajor = decltype(kmajor_tag)::value;
+                        constexpr int MN = decltype(mn_tag)::value;
+                        constexpr uint32_t lo_off = MN * 64;                             // bytes of one bf16 tile: MN x 32 elements x 2 B
 #pragma unroll 2
-                    for (int i = t; i < ROWS * 4; i += 128) {
-                        const int r = i >> 2, c2 = i & 3;                  // row (over A then B), bf16 chunk
-                        const uint32_t raw_row = hi + r * 128;
-                        const uint4 x0 = ptx::lds128(raw_row + (((2 * c2) ^ (r & 7)) << 4));
-                        const uint4 x1 = ptx::lds128(raw_row + (((2 * c2 + 1) ^ (r & 7)) << 4));
-                        const float f[8] = {__uint_as_float(x0.x), __uint_as_float(x0.y), __uint_as_float(x0.z), __uint_as_float(x0.w),
-                                            __uint_as_float(x1.x), __uint_as_float(x1.y), __uint_as_float(x1.z), __uint_as_float(x1.w)};
-                        uint4 v16, l16;
-                        __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v16);
-                        __nv_bfloat162* hl = reinterpret_cast<__nv_bfloat162*>(&l16);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float a0 = f[2 * e], a1 = f[2 * e + 1];
-                            hv[e] = __floats2bfloat162_rn(a0, a1);
-                            hl[e] = __floats2bfloat162_rn(a0 - __uint_as_float(__float_as_uint(a0) & 0xffffe000u),
-                                                          a1 - __uint_as_float(__float_as_uint(a1) & 0xffffe000u));
+                        for (int ii = t; ii < MN * 4; ii += 128) {
+                            uint4 x0, x1; uint32_t dst;
+                            if constexpr (kmajor) {
+                                const int r = ii >> 2, c2 = ii & 3;                     // MN row, 8-element K chunk
+                                x0 = ptx::lds128(raw + r * 128 + (((2 * c2) ^ (r & 7)) << 4));
+                                x1 = ptx::lds128(raw + r * 128 + (((2 * c2 + 1) ^ (r & 7)) << 4));
+                                dst = t16 + r * 64 + ((c2 ^ ((r >> 1) & 3)) << 4);
+                            } else {
+                                const int k = ii & 31, m8 = ii >> 5;                    // k row, 8-element MN chunk (mn0 = 8 * m8)
+                                const uint32_t src = raw + (m8 >> 2) * 4096 + k * 128 + (((m8 & 3) ^ (k & 3)) << 5);
+                                // the 32 lanes of a warp read 32 different k-rows: rows k and k+4 hold the same 32-byte unit slot, so they
+                                // fetch its two halves in opposite order (4-way instead of 8-way bank conflict: the optimum for 512 bytes)
+                                const uint32_t flip = ((k >> 2) & 1) << 4;
+                                const uint4 y0 = ptx::lds128(src + flip), y1 = ptx::lds128(src + (flip ^ 16));
+                                x0 = flip ? y1 : y0; x1 = flip ? y0 : y1;
+                                dst = t16 + (m8 >> 3) * 4096 + k * 128 + (((m8 & 7) ^ (k & 7)) << 4);
+                            }
+                            uint4 v16, l16;
+                            split8_bf16(x0, x1, v16, l16);
+                            ptx::sts128(dst, v16);
+                            ptx::sts128(dst + lo_off, l16);
                         }
-                        // A rows -> (A16, Alo16) tiles, B rows -> (B16, Blo16) tiles; each tile: rows * 64 bytes
-                        const bool isA = r < BM;
-                        const int rr = isA ? r : r - BM;
-                        const uint32_t t16 = lo + (isA ? 0 : Cfg::A_BYTES) + rr * 64 + ((c2 ^ ((rr >> 1) & 3)) << 4);
-                        ptx::sts128(t16, v16);
-                        ptx::sts128(t16 + (isA ? Cfg::A_BYTES : Cfg::B_BYTES) / 2, l16);
-                    }
+                    };
+                    split_operand(std::integral_constant<bool, MA == MAJOR_K>{}, std::integral_constant<int, BM>{}, hi, lo);
+                    split_operand(std::integral_constant<bool, MB == MAJOR_K>{}, std::integral_constant<int, BN / CG>{}, hi + Cfg::A_BYTES, lo + Cfg::A_BYTES);
                 } else {
 #pragma unroll 4
                 for (int i = t; i < Cfg::RAW_BYTES / 16; i += 128) {

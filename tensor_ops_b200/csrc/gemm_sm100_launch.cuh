@@ -36,11 +36,9 @@ template <typename T, int MA, int MB, int CG>
 cudaError_t launch_cg(int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
     // stage bytes: 1-pass (128 + bn/CG) * 128, 3-pass twice that; stage counts fill the 227 KiB left after the epilogue staging
     if constexpr (sizeof(T) == 4) {
-        if constexpr (MA == 0 && MB == 0) {
-            if (passes == 2) {   // TF32 hi*hi + two bf16 correction passes (K-major operands)
-                if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 4 : 3, 2, CG>(tm, p, grid, st);
-                return launch_one<T, MA, MB, 256, CG == 2 ? 3 : 2, 2, CG>(tm, p, grid, st);
-            }
+        if (passes == 2) {   // TF32 hi*hi + two bf16 correction passes
+            if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 4 : 3, 2, CG>(tm, p, grid, st);
+            return launch_one<T, MA, MB, 256, CG == 2 ? 3 : 2, 2, CG>(tm, p, grid, st);
         }
         if (passes >= 2) {
             if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 4 : 3, 3, CG>(tm, p, grid, st);

@@ -23,7 +23,7 @@ def fg(with_db, with_dx=True):
     s = [L.c_buf(A.b.value), L.c_buf(dX.b.value), L.c_buf(dW.b.value), L.c_buf(db.b.value)]
     ctx.check(L.lib.tops_fflayer_fwd_grad(ctx.h, X.b, W.b, b.b, 1, dA.b, C.byref(s[0]), C.byref(s[1]) if with_dx else None, C.byref(s[2]),
                                           C.byref(s[3]) if with_db else None))
-for prec, pn in ((tb.PREC_TF32, "tf32"), (tb.PREC_TF32X3, "tf32x3")):
+for prec, pn in ((tb.PREC_TF32, "tf32"), (tb.PREC_TF32X3, "tf32x3"), (tb.PREC_TF32_BF16X2, "tf32bf16")):
     ctx.set_precision(prec)
     run(pn + " fwd only (BIAS_ACT)", fwd_only)
     run(pn + " fwd_grad no db (DZ)", lambda: fg(False))
