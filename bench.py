@@ -57,8 +57,8 @@ def load_peaks():
 
 def ncu_traffic_bytes(tag):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` summary
-    (profiles/r1_gemm_3xtf32_ncu.csv, captured with the same bench command); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r1_gemm_3xtf32_ncu.csv")
+    (profiles/r1_gemm_parity_ncu.csv, captured with the same bench command); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_gemm_parity_ncu.csv")
     want = {"gemm_fwd": "<float, 0, 0,", "gemm_dW": "<float, 1, 1,", "gemm_dX": "<float, 0, 1,"}.get(tag)
     if not want or not os.path.exists(path):
         return None
