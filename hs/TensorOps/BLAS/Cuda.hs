@@ -40,6 +40,7 @@ import           Foreign
 import           Foreign.C.String
 import           Foreign.C.Types
 import           System.IO.Unsafe          (unsafePerformIO)
+import           Unsafe.Coerce             (unsafeCoerce)
 import           TensorOps.BLAS
 import           TensorOps.NatKind
 import qualified Data.Finite               as DF
@@ -56,6 +57,9 @@ foreign import ccall unsafe "tops_buf_alloc"   c_buf_alloc   :: Ptr Ctx -> CInt 
 foreign import ccall unsafe "&tops_buf_release" p_buf_release :: FunPtr (Ptr Buf -> IO ())
 foreign import ccall unsafe "tops_upload"      c_upload      :: Ptr Ctx -> Ptr Buf -> Ptr CFloat -> CSize -> IO CInt
 foreign import ccall safe   "tops_download"    c_download    :: Ptr Ctx -> Ptr Buf -> Ptr CFloat -> CSize -> IO CInt
+foreign import ccall unsafe "tops_buf_numel"   c_buf_numel   :: Ptr Buf -> IO Int64
+foreign import ccall unsafe "tops_buf_rank"    c_buf_rank    :: Ptr Buf -> IO CInt
+foreign import ccall unsafe "tops_buf_dims"    c_buf_dims    :: Ptr Buf -> Ptr Int64 -> IO CInt
 foreign import ccall unsafe "tops_fill"        c_fill        :: Ptr Ctx -> Ptr Buf -> CDouble -> IO CInt
 foreign import ccall unsafe "tops_axpy"        c_axpy        :: Ptr Ctx -> CDouble -> Ptr Buf -> Ptr Buf -> Ptr (Ptr Buf) -> IO CInt
 foreign import ccall unsafe "tops_dot"         c_dot         :: Ptr Ctx -> Ptr Buf -> Ptr Buf -> Ptr (Ptr Buf) -> IO CInt
@@ -254,11 +258,42 @@ instance BLAS CuMat where
     sumB (CuMat x) = Lit . scalarOf $ pureOut "tops_sum" $ \out -> withDev x $ \px -> c_sum theCtx px out
 
     -- Element-at-a-time generators / traversals (BLAS.hs:140-157; HMat.hs:176-216) are host<->device by nature:
-    -- build the host array once, one upload (bgenA) / one download + one upload (iElemsB, iRowsB).
+    -- build the host array once, one upload (bgenA) / one download + one upload (iElemsB, iRowsB, bgenRowsA).
     bgenA s f = upload (dimsOf s) <$> traverse (fmap unLit . f) (indices s)
-    bgenRowsA f = error "bgenRowsA: concatenate the generated rows with tops_buf_view + tops_axpy (see INTEGRATION.md)"
-    iRowsB _ _ = error "iRowsB: per-row traversal = tops_index_row views + bgenRowsA (see INTEGRATION.md)"
-    iElemsB f x = error "iElemsB: tops_download, traverse on the host, tops_upload (see INTEGRATION.md)"
+
+    bgenRowsA :: forall f n m. (Applicative f, SingI n) => (DF.Finite n -> f (CuMat ('BV m))) -> f (CuMat ('BM n m))
+    bgenRowsA f = stackRows <$> traverse (f . DF.finite) [0 .. fromSing (sing :: Sing n) - 1]
+
+    iRowsB f m@(CuMat d) = stackRows <$> traverse (\i -> f (DF.finite i) (indexRowB (DF.finite i) m)) [0 .. nRows - 1]
+      where nRows = fromIntegral (head (shapeOf d))
+
+    iElemsB f x@(CuMat d) = upload ds <$> traverse (\(ix, e) -> unLit <$> f ix (Lit e)) (zip (indicesOfDims ds) (download d))
+      where ds = shapeOf d
+
+-- | rows (device vectors) -> one device matrix: each row is downloaded and the matrix uploaded once (setup-time path only)
+stackRows :: [CuMat ('BV m)] -> CuMat ('BM n m)
+stackRows rows = upload [fromIntegral (length rows), fromIntegral (length (head hostRows))] (concat hostRows)
+  where hostRows = [ download d | CuMat d <- rows ]
+
+-- | logical dims of a device tensor (tops_buf_rank / tops_buf_dims)
+shapeOf :: Dev -> [Int64]
+shapeOf d = unsafePerformIO $ withDev d $ \b -> do
+    r <- c_buf_rank b
+    allocaArray (fromIntegral r) $ \pd -> c_buf_dims b pd >> peekArray (fromIntegral r) pd
+
+-- | the whole tensor as a row-major host list (tops_download synchronises)
+download :: Dev -> [Float]
+download d = unsafePerformIO $ withDev d $ \b -> do
+    n <- fromIntegral <$> c_buf_numel b
+    allocaArray n $ \p -> do
+      check "tops_download" =<< c_download theCtx b p (fromIntegral (4 * n))
+      map realToFrac <$> peekArray n p
+
+indicesOfDims :: [Int64] -> [BShapeP DF.Finite s]
+indicesOfDims = \case
+    [n]    -> unsafeCoerce [ PBV (DF.finite (fromIntegral i)) | i <- [0 .. n - 1] ]
+    [n, m] -> unsafeCoerce [ PBM (DF.finite (fromIntegral i)) (DF.finite (fromIntegral j)) | i <- [0 .. n - 1], j <- [0 .. m - 1] ]
+    _      -> error "indicesOfDims: BLAS shapes are vectors or matrices"
 
 unLit :: Sc -> Float
 unLit (Lit v) = v
