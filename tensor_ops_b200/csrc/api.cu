@@ -764,15 +764,32 @@ int layer_shapes(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops
     return TOPS_OK;
 }
 
+// TOPS_PREC_TF32_BF16X2: the small operand W takes part in two GEMMs of a layer (forward and dX); its bf16 correction operands
+// bf16(W), bf16(W - trunc_tf32(W)) are produced once per call in HBM (4 extra bytes per weight) so that the GEMMs' splitter warps
+// only re-tile the big operand.  Leaves NULL pointers when the mode / shape does not apply.
+struct WSplit { const void* w16 = nullptr; const void* wlo16 = nullptr; };
+int make_wsplit(tops_ctx* ctx, const tops_buf* W, Tmp& tmp, WSplit* out) {
+    if (ctx->precision != TOPS_PREC_TF32_BF16X2 || W->dtype != TOPS_F32 || W->tr || W->rank != 2 || (W->dims[1] % 8) != 0 || W->numel == 0) return TOPS_OK;
+    tops_buf *a = nullptr, *b = nullptr;
+    TRY(alloc_buf(ctx, TOPS_BF16, 2, W->dims, &a)); tmp.keep(a);
+    TRY(alloc_buf(ctx, TOPS_BF16, 2, W->dims, &b)); tmp.keep(b);
+    k::split_bf16(lc_of(ctx), (const float*)W->data, a->data, b->data, W->numel);
+    TRY(check_launch(ctx, "split_bf16"));
+    out->w16 = a->data; out->wlo16 = b->data;
+    return TOPS_OK;
+}
+
 // A = act(X W^T + b)  [optionally also dZ = dA ⊙ act'(A)]  — one GEMM, everything else in its epilogue
 // `db` (optional, epilogues with a dZ output only): column sums of dZ fused into the epilogue; *db_fused reports whether the
 // kernel produced them (the TMA epilogue does; the direct / SIMT paths leave it to col_sums).
 int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, const float* b, int act, int epi,
-             void* A, const void* aux, void* out1, float* loss, float* db = nullptr, int* db_fused = nullptr, bool db_accumulate = false) {
+             void* A, const void* aux, void* out1, float* loss, float* db = nullptr, int* db_fused = nullptr, bool db_accumulate = false,
+             const WSplit* ws = nullptr) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.o; g.K = (int)s.i;
     g.A = X; g.lda = s.i; g.major_a = MAJOR_K;
     g.B = W; g.ldb = s.i; g.major_b = MAJOR_K;
+    if (ws) { g.B16 = ws->w16; g.Blo16 = ws->wlo16; }
     g.epi = epi; g.act = act; g.alpha = 1.f; g.bias = b; g.tag = "gemm_fwd";
     g.out0 = A; g.ld_out0 = s.o; g.out1 = out1; g.ld_out1 = s.o; g.aux0 = aux; g.ld_aux0 = s.o; g.loss = loss;
     g.io_bf16 = g.dtype;
@@ -789,11 +806,12 @@ int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, 
 // dX = dZ W  (optionally ⊙ act'(A_prev))
 // `db_prev` (optional, EPI_MUL_DACT only): the output IS dZ of the previous layer, so its column sums are that layer's db.
 int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, void* dX, int epi, int act, const void* Aprev,
-            float* db_prev = nullptr, int* db_fused = nullptr) {
+            float* db_prev = nullptr, int* db_fused = nullptr, const WSplit* ws = nullptr) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.i; g.K = (int)s.o;
     g.A = dZ; g.lda = s.o; g.major_a = MAJOR_K;
     g.B = W; g.ldb = s.i; g.major_b = MAJOR_MN;
+    if (ws) { g.B16 = ws->w16; g.Blo16 = ws->wlo16; }
     g.epi = epi; g.act = act; g.alpha = 1.f; g.tag = "gemm_dX";
     g.out0 = dX; g.ld_out0 = s.i; g.aux0 = Aprev; g.ld_aux0 = s.i;
     g.io_bf16 = g.dtype;
@@ -861,11 +879,12 @@ extern "C" int tops_fflayer_fwd_grad(tops_ctx* ctx, const tops_buf* X, const top
     if (db) TRY(prep_out(ctx, db, TOPS_F32, 1, dbs));
     Tmp tmp; tops_buf* dZ = nullptr;
     TRY(alloc_buf(ctx, s.dtype, 2, dAo, &dZ)); tmp.keep(dZ);
+    WSplit ws; TRY(make_wsplit(ctx, W, tmp, &ws));
     int db_fused = 0;
     TRY(fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, (*A)->data, dA->data, dZ->data, nullptr,
-                 db ? (float*)(*db)->data : nullptr, &db_fused));
+                 db ? (float*)(*db)->data : nullptr, &db_fused, false, &ws));
     TRY(dw_db(ctx, s, dZ->data, X->data, (float*)(*dW)->data, db ? (float*)(*db)->data : nullptr, db_fused != 0));
-    if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
+    if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr, nullptr, nullptr, &ws));
     return TOPS_OK;
 }
 
@@ -910,7 +929,8 @@ extern "C" int tops_fflayer_fwd_grad_host(tops_ctx* ctx, const float* X_host, co
         cudaEventRecord(e, ctx->copy_stream);
         ev.push_back(e);
     }
-    int rc = TOPS_OK;
+    WSplit ws;
+    int rc = make_wsplit(ctx, W, tmp, &ws);
     int64_t r0 = 0;
     for (size_t c = 0; c < ev.size() && rc == TOPS_OK; ++c, r0 += rows_per) {
         const int64_t n = (B - r0 < rows_per) ? B - r0 : rows_per;
@@ -919,9 +939,9 @@ extern "C" int tops_fflayer_fwd_grad_host(tops_ctx* ctx, const float* X_host, co
         const float* Xc = (const float*)Xd->data + r0 * i; const float* dAc = (const float*)dAd->data + r0 * o;
         float* Ac = (float*)Ad->data + r0 * o; float* dZc = (float*)dZ->data + r0 * o; float* dXc = (float*)dXd->data + r0 * i;
         int fused = 0;
-        rc = fwd_gemm(ctx, s, Xc, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, Ac, dAc, dZc, nullptr, db, &fused, true);
+        rc = fwd_gemm(ctx, s, Xc, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, Ac, dAc, dZc, nullptr, db, &fused, true, &ws);
         if (rc == TOPS_OK) rc = dw_db(ctx, s, dZc, Xc, dW, db, fused != 0, true);
-        if (rc == TOPS_OK) rc = dx_gemm(ctx, s, dZc, W->data, dXc, EPI_STORE, ACT_ID, nullptr);
+        if (rc == TOPS_OK) rc = dx_gemm(ctx, s, dZc, W->data, dXc, EPI_STORE, ACT_ID, nullptr, nullptr, nullptr, &ws);
     }
     for (auto e : ev) cudaEventDestroy(e);
     cudaEventDestroy(ready);
@@ -954,12 +974,13 @@ extern "C" int tops_fflayer_fwd_grad_mc(tops_ctx* ctx, const tops_buf* X, const 
     float* dW_mc = (float*)grads_mc; float* db_mc = dW_mc + s.o * s.i;
     Tmp tmp; tops_buf* dZ = nullptr;
     TRY(alloc_buf(ctx, s.dtype, 2, dAo, &dZ)); tmp.keep(dZ);
+    WSplit ws; TRY(make_wsplit(ctx, W, tmp, &ws));
     int db_fused = 0;
-    TRY(fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, (*A)->data, dA->data, dZ->data, nullptr, db, &db_fused));
+    TRY(fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, (*A)->data, dA->data, dZ->data, nullptr, db, &db_fused, false, &ws));
     TRY(dw_db(ctx, s, dZ->data, X->data, dW, db, db_fused != 0, false, dW_mc));
     k::mc_push(lc_of(ctx), db, db_mc, s.o);            // o floats: the bias gradient joins the same multicast buffer
     TRY(check_launch(ctx, "mc_push"));
-    if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
+    if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr, nullptr, nullptr, &ws));
     return TOPS_OK;
 }
 

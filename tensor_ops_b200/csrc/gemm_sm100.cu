@@ -87,7 +87,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     int cg = c.cta_group;
     if (cg == 0) cg = (c.M > 128) ? 2 : 1;
     if (cg != 1 && cg != 2) return fail(-1, "gemm: cta_group must be 0 (auto), 1 or 2");
-    CUtensorMap tm[3];   // A, B, aux0
+    CUtensorMap tm[5];   // A, B, aux0, bf16(B), bf16(B_lo)
     CUtensorMap &ta = tm[0], &tb = tm[1];
     memset(tm, 0, sizeof tm);
     bool ok;
@@ -109,7 +109,15 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
         tma_epi = aligned(c.out0, c.ld_out0) && (!has_out1 || aligned(c.out1, c.ld_out1));
         if (tma_epi && has_aux) tma_epi = make_map(&tm[2], c.io_bf16 ? 1 : 0, c.aux0, c.N, c.M, c.ld_aux0, 32, 32, c.io_bf16 ? SWZ_64 : SWZ_128);
     }
+    // passes == 2 with a pre-split B: two more maps delivering the bf16 tiles in the layouts the splitter would have produced
+    // (K-major: 64-byte rows, SWIZZLE_64B; MN-major: [32 k-rows x 64 elements], SWIZZLE_128B)
+    bool b_presplit = false;
+    if (passes == 2 && c.B16 && c.Blo16) {
+        if (c.major_b == MAJOR_K) b_presplit = make_map(&tm[3], 1, c.B16, c.K, c.N, c.ldb, 32, bn / cg, SWZ_64) && make_map(&tm[4], 1, c.Blo16, c.K, c.N, c.ldb, 32, bn / cg, SWZ_64);
+        else b_presplit = make_map(&tm[3], 1, c.B16, c.N, c.K, c.ldb, 64, 32, SWZ_128) && make_map(&tm[4], 1, c.Blo16, c.N, c.K, c.ldb, 64, 32, SWZ_128);
+    }
     GemmParams p{};
+    p.b_presplit = b_presplit ? 1 : 0;
     p.M = c.M; p.N = c.N; p.K = c.K;
     p.num_m_tiles = (c.M + 128 * cg - 1) / (128 * cg);
     p.num_n_tiles = (c.N + bn - 1) / bn;

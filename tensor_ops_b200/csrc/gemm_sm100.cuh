@@ -72,6 +72,7 @@ struct GemmParams {
     int* tile_counters;       // [num_tiles * CG * 8] zeroed by the caller
     int io_bf16;              // out0/out1/aux0 are bf16 (bf16 pipelines); 0 = fp32
     int vec_ok;               // 16-byte vector access legal for out0/out1/aux0
+    int b_presplit;           // PASSES == 2: bf16(B) and bf16(B_lo) exist in HBM (tmB16 / tmBlo16): TMA loads them, the splitter handles A only
     int tma_epi;              // staged epilogue: outputs via smem staging + coalesced stores, aux operand by TMA (tmAux valid if needed)
     unsigned int* watchdog;   // mapped host memory, 2 words
 };
@@ -493,7 +494,7 @@ __device__ __forceinline__ void split4_bf16(const uint4& x, uint2& v8, uint2& l8
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
 __global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>::NUM_THREADS), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAux,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB16, const __grid_constant__ CUtensorMap tmBlo16, const GemmParams p) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
     constexpr bool kBF16 = sizeof(T) == 2;
     constexpr bool kChunked = PASSES >= 2;   // TMEM holds one chunk; the running sum lives in epilogue registers
@@ -527,6 +528,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
         if (p.tma_epi && epi_has_aux(p)) ptx::prefetch_tensormap(&tmAux);
+        if (PASSES == 2 && p.b_presplit) { ptx::prefetch_tensormap(&tmB16); ptx::prefetch_tensormap(&tmBlo16); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -572,7 +574,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if constexpr (CG == 2) ptx::mbar_wait_cluster(&empty_bar[s], ph ^ 1, wd, 0x100 + s);
                     else ptx::mbar_wait(&empty_bar[s], ph ^ 1, wd, 0x100 + s);
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::RAW_BYTES);
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::RAW_BYTES + ((PASSES == 2 && p.b_presplit) ? Cfg::B_BYTES : 0));
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     if constexpr (MA == MAJOR_K) {
@@ -588,6 +590,22 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int r = 0; r < (BN / CG) / KB; ++r)
                             ptx::tma_load_2d(sb + r * (KB * 128), &tmB, &full_bar[s], n0 + r * KB, kb * KB);
+                    }
+                    if constexpr (PASSES == 2) {
+                        if (p.b_presplit) {   // the small operand was split once in HBM: its bf16 tiles arrive ready-made
+                            uint8_t* b16 = sa + Cfg::RAW_BYTES + Cfg::A_BYTES;
+                            uint8_t* blo16 = b16 + Cfg::B_BYTES / 2;
+                            if constexpr (MB == MAJOR_K) {
+                                ptx::tma_load_2d(b16, &tmB16, &full_bar[s], kb * KB, n0);
+                                ptx::tma_load_2d(blo16, &tmBlo16, &full_bar[s], kb * KB, n0);
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < (BN / CG) / 64; ++r) {
+                                    ptx::tma_load_2d(b16 + r * 4096, &tmB16, &full_bar[s], n0 + r * 64, kb * KB);
+                                    ptx::tma_load_2d(blo16 + r * 4096, &tmBlo16, &full_bar[s], n0 + r * 64, kb * KB);
+                                }
+                            }
+                        }
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -887,7 +905,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     };
                     split_operand(std::integral_constant<bool, MA == MAJOR_K>{}, std::integral_constant<int, BM>{}, hi, lo);
-                    split_operand(std::integral_constant<bool, MB == MAJOR_K>{}, std::integral_constant<int, BN / CG>{}, hi + Cfg::A_BYTES, lo + Cfg::A_BYTES);
+                    if (!p.b_presplit)
+                        split_operand(std::integral_constant<bool, MB == MAJOR_K>{}, std::integral_constant<int, BN / CG>{}, hi + Cfg::A_BYTES, lo + Cfg::A_BYTES);
                 } else {
 #pragma unroll 4
                 for (int i = t; i < Cfg::RAW_BYTES / 16; i += 128) {

@@ -12,6 +12,7 @@ struct GemmCall {
     int M, N, K;
     const void* A; long long lda; int major_a;   // 0: A stored [M,K] (K contiguous), 1: stored [K,M]
     const void* B; long long ldb; int major_b;   // 0: B stored [N,K] (K contiguous), 1: stored [K,N]
+    const void* B16; const void* Blo16;   // optional (passes == 2): bf16(B) and bf16(B - trunc_tf32(B)), same shape / ldb as B, pre-split in HBM
     int epi, act;
     float alpha, beta;
     void* out0; long long ld_out0;

@@ -19,7 +19,7 @@ cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cud
         attr_set = true;
     }
     if constexpr (CG == 1) {
-        kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], p);
+        kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
         return cudaGetLastError();
     } else {
         cudaLaunchConfig_t cfg{};
@@ -28,7 +28,7 @@ cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cud
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], p);
+        return cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], tm[4], p);
     }
 }
 

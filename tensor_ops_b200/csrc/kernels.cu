@@ -489,6 +489,22 @@ void mc_push(const LaunchCtx& lc, const float* src, float* out_mc, int64_t n) {
     count(lc);
 }
 
+namespace {
+__global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ lo, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float a = x[i];
+        v[i] = __float2bfloat16_rn(a);
+        lo[i] = __float2bfloat16_rn(a - __uint_as_float(__float_as_uint(a) & 0xffffe000u));
+    }
+}
+}  // namespace
+void split_bf16(const LaunchCtx& lc, const float* x, void* v, void* lo, int64_t n) {
+    if (n <= 0) return;
+    k_split_bf16<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(x, (__nv_bfloat16*)v, (__nv_bfloat16*)lo, n);
+    count(lc);
+}
+
 void fill(const LaunchCtx& lc, float* p, int64_t n, float v) { if (n <= 0) return; k_fill<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(p, n, v); count(lc); }
 void fill_bf16(const LaunchCtx& lc, void* p, int64_t n, float v) { if (n <= 0) return; k_fill_bf16<<<grid_for(lc, n), kThreads, 0, lc.stream>>>((__nv_bfloat16*)p, n, v); count(lc); }
 void rand_normal(const LaunchCtx& lc, float* p, int64_t n, float mean, float sd, uint64_t seed) { if (n <= 0) return; k_rand<true><<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(p, n, mean, sd, seed); count(lc); }

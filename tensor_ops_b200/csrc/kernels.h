@@ -23,6 +23,8 @@ void rand_normal(const LaunchCtx&, float* p, int64_t n, float mean, float sd, ui
 void rand_uniform(const LaunchCtx&, float* p, int64_t n, float lo, float hi, uint64_t seed);
 void cast_f32_bf16(const LaunchCtx&, const float* s, void* d, int64_t n);
 void cast_bf16_f32(const LaunchCtx&, const void* s, float* d, int64_t n);
+// v[i] = bf16(x[i]), lo[i] = bf16(x[i] - trunc_tf32(x[i]))  (operands of the bf16 correction passes, TOPS_PREC_TF32_BF16X2)
+void split_bf16(const LaunchCtx&, const float* x, void* v, void* lo, int64_t n);
 void eye(const LaunchCtx&, float* p, int64_t n);
 
 // ---- elementwise
