@@ -864,7 +864,8 @@ extern "C" int tops_fflayer_fwd(tops_ctx* ctx, const tops_buf* X, const tops_buf
     LayerShapes s; TRY(layer_shapes(ctx, X, W, b, &s)); TRY(check_act(ctx, act));
     int64_t d[2] = {s.B, s.o};
     TRY(prep_out(ctx, A, s.dtype, 2, d));
-    return fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT, (*A)->data, nullptr, nullptr, nullptr);
+    Tmp tmp; WSplit ws; TRY(make_wsplit(ctx, W, tmp, &ws));
+    return fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT, (*A)->data, nullptr, nullptr, nullptr, nullptr, nullptr, false, &ws);
 }
 
 extern "C" int tops_fflayer_fwd_grad(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act,
@@ -1025,19 +1026,20 @@ int mlp_check(tops_ctx* ctx, int n, const tops_buf* const* W, const tops_buf* co
 }
 
 // one forward layer: returns Z (only for softmax, else NULL) and A
-int mlp_layer_fwd(tops_ctx* ctx, const tops_buf* in, const tops_buf* W, const tops_buf* b, int act, Tmp& tmp, tops_buf** Zout, tops_buf* A) {
+int mlp_layer_fwd(tops_ctx* ctx, const tops_buf* in, const tops_buf* W, const tops_buf* b, int act, Tmp& tmp, tops_buf** Zout, tops_buf* A,
+                  const WSplit* ws = nullptr) {
     LayerShapes s{in->dims[0], in->dims[1], W->dims[0], TOPS_F32};
     *Zout = nullptr;
     if (act == TOPS_ACT_SOFTMAX) {
         int64_t d[2] = {s.B, s.o};
         tops_buf* Z = nullptr;
         TRY(alloc_buf(ctx, TOPS_F32, 2, d, &Z)); tmp.keep(Z);
-        TRY(fwd_gemm(ctx, s, in->data, W->data, (const float*)b->data, ACT_ID, EPI_BIAS_ACT, Z->data, nullptr, nullptr, nullptr));
+        TRY(fwd_gemm(ctx, s, in->data, W->data, (const float*)b->data, ACT_ID, EPI_BIAS_ACT, Z->data, nullptr, nullptr, nullptr, nullptr, nullptr, false, ws));
         if (A) { k::softmax_rows(lc_of(ctx), (const float*)Z->data, (float*)A->data, s.B, s.o); TRY(check_launch(ctx, "softmax")); }
         *Zout = Z;
         return TOPS_OK;
     }
-    return fwd_gemm(ctx, s, in->data, W->data, (const float*)b->data, act, EPI_BIAS_ACT, A->data, nullptr, nullptr, nullptr);
+    return fwd_gemm(ctx, s, in->data, W->data, (const float*)b->data, act, EPI_BIAS_ACT, A->data, nullptr, nullptr, nullptr, nullptr, nullptr, false, ws);
 }
 
 }  // namespace
@@ -1053,7 +1055,8 @@ extern "C" int tops_mlp_fwd(tops_ctx* ctx, int n, const tops_buf* const* W, cons
         if (l == n - 1) { TRY(prep_out(ctx, A_out, TOPS_F32, 2, d)); A = *A_out; }
         else { TRY(alloc_buf(ctx, TOPS_F32, 2, d, &A)); tmp.keep(A); }
         tops_buf* Z;
-        TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Z, A));
+        WSplit ws; TRY(make_wsplit(ctx, W[l], tmp, &ws));
+        TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Z, A, &ws));
         cur = A;
     }
     return TOPS_OK;
@@ -1074,6 +1077,8 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
     TRY(prep_out(ctx, loss_sum, TOPS_F32, 0, nullptr));
     float* lossp = (float*)(*loss_sum)->data;
     CUDA_TRY(ctx, cudaMemsetAsync(lossp, 0, 4, ctx->stream));
+    std::vector<WSplit> wsp(n);   // bf16 correction operands of every W: used by its forward GEMM and its dX GEMM
+    for (int l = 0; l < n; ++l) TRY(make_wsplit(ctx, W[l], tmp, &wsp[l]));
     // gradient outputs first: the GEMM epilogues that produce a dZ also produce that layer's db (fused column sums)
     std::vector<int> db_done(n, 0);
     for (int l = 0; l < n; ++l) {
@@ -1095,13 +1100,13 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
         if (last && acts[l] != TOPS_ACT_SOFTMAX && loss == TOPS_LOSS_SQUARED_ERROR) {
             LayerShapes s{B, cur->dims[1], d[1], TOPS_F32};
             TRY(fwd_gemm(ctx, s, cur->data, W[l]->data, (const float*)b[l]->data, acts[l], EPI_BIAS_ACT_SE, A->data, Y->data, dZ->data, lossp,
-                         (float*)db[l]->data, &db_done[l]));
+                         (float*)db[l]->data, &db_done[l], false, &wsp[l]));
         } else if (last && acts[l] == TOPS_ACT_SOFTMAX && loss == TOPS_LOSS_CROSS_ENTROPY) {
-            TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], nullptr));
+            TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], nullptr, &wsp[l]));
             k::softmax_ce_rows(lc_of(ctx), (const float*)Zs[l]->data, (const float*)Y->data, (float*)A->data, (float*)dZ->data, lossp, B, d[1]);
             TRY(check_launch(ctx, "softmax_ce"));
         } else {
-            TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], A));
+            TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], A, &wsp[l]));
             if (last) {   // generic head: loss VJP on activations, then the activation's VJP
                 tops_buf* dA = nullptr;
                 TRY(alloc_buf(ctx, TOPS_F32, 2, d, &dA)); tmp.keep(dA);
@@ -1124,18 +1129,18 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
             if (acts[l - 1] == TOPS_ACT_SOFTMAX) {
                 tops_buf* dAp = nullptr;
                 TRY(alloc_buf(ctx, TOPS_F32, 2, d, &dAp)); tmp.keep(dAp);
-                TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, dAp->data, EPI_STORE, ACT_ID, nullptr));
+                TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, dAp->data, EPI_STORE, ACT_ID, nullptr, nullptr, nullptr, &wsp[l]));
                 k::softmax_vjp_rows(lc_of(ctx), (const float*)Zs[l - 1]->data, (const float*)dAp->data, (float*)dZp->data, B, s.i);
                 TRY(check_launch(ctx, "softmax_vjp"));
             } else {
                 TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, dZp->data, EPI_MUL_DACT, acts[l - 1], acts_in[l]->data,
-                            (float*)db[l - 1]->data, &db_done[l - 1]));
+                            (float*)db[l - 1]->data, &db_done[l - 1], &wsp[l]));
             }
             dZ = dZp;
         } else if (dX) {
             int64_t d[2] = {B, s.i};
             TRY(prep_out(ctx, dX, TOPS_F32, 2, d));
-            TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr));
+            TRY(dx_gemm(ctx, s, dZ->data, W[l]->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr, nullptr, nullptr, &wsp[l]));
         }
     }
     return TOPS_OK;
