@@ -92,6 +92,10 @@ int tops_buf_dims(const tops_buf* b, int64_t* dims_out);   /* writes rank entrie
 int tops_buf_dtype(const tops_buf* b);
 int64_t tops_buf_numel(const tops_buf* b);
 void* tops_buf_data(const tops_buf* b);                     /* device pointer */
+/* page-locked host staging memory for upload / download / the host-buffer entry points (full PCIe rate, asynchronous copies);
+ * write_combined = 1 asks for write-combined pages: faster for the device to read, slow for the CPU to READ (fill it, don't read it) */
+int tops_host_alloc(size_t bytes, int write_combined, void** out);
+int tops_host_free(void* p);
 int tops_upload(tops_ctx* ctx, tops_buf* dst, const void* host, size_t bytes);      /* H2D, async if host is pinned */
 int tops_download(tops_ctx* ctx, const tops_buf* src, void* host, size_t bytes);    /* D2H + stream sync */
 int tops_fill(tops_ctx* ctx, tops_buf* dst, double value);                          /* TT.konst, Tensor.hs:49-54 */

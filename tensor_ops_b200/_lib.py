@@ -46,6 +46,8 @@ PROTOTYPES = {
     "tops_buf_dtype": (C.c_int, [c_buf]),
     "tops_buf_numel": (C.c_int64, [c_buf]),
     "tops_buf_data": (C.c_void_p, [c_buf]),
+    "tops_host_alloc": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "tops_host_free": (C.c_int, [C.c_void_p]),
     "tops_upload": (C.c_int, [c_ctx, c_buf, C.c_void_p, C.c_size_t]),
     "tops_download": (C.c_int, [c_ctx, c_buf, C.c_void_p, C.c_size_t]),
     "tops_fill": (C.c_int, [c_ctx, c_buf, C.c_double]),

@@ -365,6 +365,17 @@ extern "C" int tops_buf_dtype(const tops_buf* b) { return b ? b->dtype : -1; }
 extern "C" int64_t tops_buf_numel(const tops_buf* b) { return b ? b->numel : -1; }
 extern "C" void* tops_buf_data(const tops_buf* b) { return b ? b->data : nullptr; }
 
+extern "C" int tops_host_alloc(size_t bytes, int write_combined, void** out) {
+    if (!out) return TOPS_ERR_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? TOPS_ERR_OOM : TOPS_ERR_CUDA; }
+    return TOPS_OK;
+}
+extern "C" int tops_host_free(void* p) {
+    if (!p) return TOPS_ERR_INVALID;
+    return cudaFreeHost(p) == cudaSuccess ? TOPS_OK : TOPS_ERR_CUDA;
+}
 extern "C" int tops_upload(tops_ctx* ctx, tops_buf* dst, const void* host, size_t bytes) {
     CHECK_CTX(ctx); LOCK(ctx);
     if (!dst || (!host && bytes)) return set_err(ctx, TOPS_ERR_INVALID, "tops_upload: NULL argument");

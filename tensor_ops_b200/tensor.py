@@ -80,6 +80,18 @@ class Context:
         self.check(L.lib.tops_rand_uniform(self.h, t.b, lo, hi, seed))
         return t
 
+    def host_empty(self, shape, write_combined: bool = False) -> np.ndarray:
+        """A float32 NumPy array over page-locked host memory (tops_host_alloc): the staging buffer for `upload` / the host-buffer
+        entry points.  write_combined=True: faster for the GPU to read over PCIe, very slow for the CPU to read back."""
+        n = int(np.prod(shape)) if len(shape) else 1
+        p = C.c_void_p()
+        self.check(L.lib.tops_host_alloc(C.c_size_t(4 * max(n, 1)), int(write_combined), C.byref(p)))
+        buf = (C.c_float * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.float32, count=n).reshape(shape)
+        self._host_blocks = getattr(self, "_host_blocks", [])
+        self._host_blocks.append(_HostBlock(p.value, buf))      # freed when the context object goes away
+        return arr
+
     def wrap(self, device_ptr: int, dims, dtype: int = L.F32, keepalive=None) -> "CuTensor":
         """Non-owning view of caller-allocated device memory (e.g. a torch tensor's storage)."""
         d = (C.c_int64 * max(1, len(dims)))(*dims)
@@ -97,6 +109,17 @@ class Context:
 
 
 _default: Optional[Context] = None
+
+
+class _HostBlock:
+    def __init__(self, ptr, buf):
+        self.ptr, self.buf = ptr, buf
+
+    def __del__(self):
+        try:
+            L.lib.tops_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
 
 
 def default_context() -> Context:

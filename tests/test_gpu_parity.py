@@ -431,3 +431,14 @@ def test_cta_pair_tile_edges(ctx, prec, B):
     got = nn.fflayer_fwd_grad(ctx.from_numpy(X), ctx.from_numpy(W), ctx.from_numpy(b), ctx.from_numpy(dA))
     for name, t, r in zip(("A", "dX", "dW", "db"), got, ref):
         close(t, r, TOL[prec], f"{name} B={B}")
+
+
+def test_pinned_host_staging_buffers(ctx):
+    """tops_host_alloc: page-locked (optionally write-combined) staging memory for upload / the host-buffer entry point."""
+    rng = np.random.default_rng(3)
+    for wc in (False, True):
+        h = ctx.host_empty((37, 24), write_combined=wc)
+        src = rng.standard_normal((37, 24)).astype(np.float32)
+        h[...] = src
+        t = ctx.empty((37, 24)).upload(h, sync=True)
+        assert np.array_equal(t.numpy(), src)
