@@ -64,7 +64,8 @@ int set_err(tops_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
-#define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu)
+// serialise calls on the context and make its device current (a process may hold contexts on several devices)
+#define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu); cudaSetDevice((ctx)->device)
 #define CHECK_CTX(ctx) do { if (!(ctx)) return TOPS_ERR_INVALID; } while (0)
 #define CUDA_TRY(ctx, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return set_err(ctx, TOPS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
 #define TRY(expr) do { int r_ = (expr); if (r_ != TOPS_OK) return r_; } while (0)

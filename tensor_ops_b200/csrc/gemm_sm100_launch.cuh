@@ -12,11 +12,14 @@ template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
 cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
     auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES, CG>;
-    static bool attr_set = false;   // per instantiation
-    if (!attr_set) {
+    // opt in to > 48 KiB of dynamic shared memory: once per (instantiation, device) — the attribute is per device
+    static unsigned long long attr_done_mask = 0;   // bit d = done on device d (racing threads at worst repeat the idempotent call)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !((attr_done_mask >> dev) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev < 64) attr_done_mask |= 1ull << dev;
     }
     if constexpr (CG == 1) {
         kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);

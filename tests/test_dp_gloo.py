@@ -79,3 +79,9 @@ def test_packed_layout_offsets():
     v = lay.views(a)
     v[2][...] = -1
     assert (a[16:24] == -1).all()          # views alias the packed buffer
+
+
+def test_fused_allreduce_needs_a_process_group():
+    """dp.FusedGradAllReduce (NVLS symmetric memory) must fail loudly, not silently degrade, outside a distributed job."""
+    with pytest.raises(RuntimeError):
+        dp.FusedGradAllReduce(16, torch.device("cpu"))
