@@ -50,8 +50,11 @@ typedef enum {
     TOPS_PREC_TF32X3 = 0,  /* 3-pass hi/lo TF32 split on tcgen05 (hi*hi + lo*hi + hi*lo), fp32-grade accuracy (~1.5e-6 rel) */
     TOPS_PREC_TF32 = 1,    /* single TF32 pass on tcgen05 (~1e-3 rel), the throughput mode                   */
     TOPS_PREC_FP32_SIMT = 2, /* CUDA-core FFMA kernel (exact fp32 products); also what un-TMA-able strides use */
-    TOPS_PREC_TF32_BF16X2 = 3 /* default: hi*hi in TF32 + the two first-order corrections bf16(lo)*bf16(x) as bf16 MMAs (half the cost of a
+    TOPS_PREC_TF32_BF16X2 = 3, /* hi*hi in TF32 + the two first-order corrections bf16(lo)*bf16(x) as bf16 MMAs (half the cost of a
                                  TF32 pass each): fp32-grade accuracy (~1.4e-6 rel) at 2 tensor-core passes instead of 3 */
+    TOPS_PREC_F16X3 = 4       /* default: every fp32 operand is stored once as an fp16 PAIR (hi, lo) of x * 2^k (22 bits of mantissa, k per
+                                 tensor or per row) and the product is three fp16 tcgen05 passes hi*hi + lo*hi + hi*lo with fp32
+                                 accumulation: ~6e-7 rel at 1.5 TF32-pass equivalents (fp16 MMAs run at twice the TF32 rate) */
 } tops_precision;
 
 typedef enum { TOPS_ACT_ID = 0, TOPS_ACT_LOGISTIC = 1, TOPS_ACT_SOFTMAX = 2 } tops_act;

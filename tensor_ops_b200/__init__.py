@@ -9,14 +9,14 @@ Layout
   top.py           TOp, Category composition, routing, primitive TOps   (Types.hs:122-264, TOp.hs)
   nn.py            activations, losses, Network/ffLayer/genNet, fused batched entry points (Learn/NeuralNet*.hs)
   batched.py       BatchT: vmap-style `instance Tensor` with lazy outer products
-  dist.py          data-parallel step: batch sharded over ranks, one all-reduce of [dW‖db]
+  dp.py            data-parallel step: batch sharded over ranks, one all-reduce of [dW‖db]
 """
 from . import _lib
 from ._lib import (ACT_ID, ACT_LOGISTIC, ACT_SOFTMAX, BF16, F32, LOSS_CROSS_ENTROPY, LOSS_SQUARED_ERROR,
-                   PREC_FP32_SIMT, PREC_TF32, PREC_TF32X3, PREC_TF32_BF16X2, TopsError)
+                   PREC_F16X3, PREC_FP32_SIMT, PREC_TF32, PREC_TF32X3, PREC_TF32_BF16X2, TopsError)
 from .tensor import Context, CuTensor, default_context
 from . import expr, top, nn, batched
 
 __all__ = ["Context", "CuTensor", "default_context", "expr", "top", "nn", "batched", "TopsError",
-           "F32", "BF16", "PREC_TF32X3", "PREC_TF32", "PREC_FP32_SIMT", "PREC_TF32_BF16X2", "ACT_ID", "ACT_LOGISTIC", "ACT_SOFTMAX",
+           "F32", "BF16", "PREC_TF32X3", "PREC_TF32", "PREC_FP32_SIMT", "PREC_TF32_BF16X2", "PREC_F16X3", "ACT_ID", "ACT_LOGISTIC", "ACT_SOFTMAX",
            "LOSS_SQUARED_ERROR", "LOSS_CROSS_ENTROPY"]

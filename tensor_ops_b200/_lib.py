@@ -92,7 +92,7 @@ for _name, (_res, _args) in PROTOTYPES.items():
 
 # enums (include/tops_b200.h)
 F32, BF16 = 0, 1
-PREC_TF32X3, PREC_TF32, PREC_FP32_SIMT, PREC_TF32_BF16X2 = 0, 1, 2, 3
+PREC_TF32X3, PREC_TF32, PREC_FP32_SIMT, PREC_TF32_BF16X2, PREC_F16X3 = 0, 1, 2, 3, 4
 ACT_ID, ACT_LOGISTIC, ACT_SOFTMAX = 0, 1, 2
 LOSS_NONE, LOSS_SQUARED_ERROR, LOSS_CROSS_ENTROPY = 0, 1, 2
 OK = 0

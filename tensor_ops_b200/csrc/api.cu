@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -25,8 +26,14 @@ struct tops_ctx {
     cudaStream_t stream = nullptr;
     std::recursive_mutex mu;
     std::string last_error;
-    int precision = TOPS_PREC_TF32_BF16X2;
+    int precision = TOPS_PREC_F16X3;
     int fused_chunk_kb = 8;
+    // F16X3: k-blocks of 64 K-elements (12 MMAs) per TMEM chunk.  The forward GEMM's error is amplified ~4x by act' at a saturating
+    // init, so it drains every 2 k-blocks (6e-7); the gradient GEMMs every 4 (1.1e-6, 7 % faster).  TOPS_F16X3_CHUNK / _FWD_CHUNK override.
+    int f16x3_chunk_kb = 4;
+    int f16x3_fwd_chunk_kb = 2;
+    struct SplitEntry { const void* src; int64_t rows, cols; void* hi; void* lo; long long ld; float* scale2; };
+    struct SplitScope* split_scope = nullptr;   // fp16 pairs already made inside the current API call
     int64_t launches = 0;
     unsigned int* wd_host = nullptr;
     unsigned int* wd_dev = nullptr;
@@ -182,10 +189,73 @@ int need_f32(tops_ctx* ctx, const tops_buf* x, const char* what) {
 }
 
 // ---------------------------------------------------------------------------------------------- GEMM dispatch
+// F16X3: an fp32 [rows, cols] operand as an fp16 pair of x * 2^k with one k for the whole tensor (absmax + split passes).  Within
+// one API call (SplitScope) the pair of a given buffer is made once and reused by every GEMM that reads it.
+}  // namespace
+struct SplitScope {
+    tops_ctx* ctx; std::vector<tops_ctx::SplitEntry> entries; Tmp keep; bool owner;
+    explicit SplitScope(tops_ctx* c) : ctx(c), owner(c->split_scope == nullptr) { if (owner) c->split_scope = this; }
+    ~SplitScope() { if (owner) ctx->split_scope = nullptr; }
+};
+namespace {
+constexpr int kF16X3Fallback = -1000;   // the operands cannot be expressed: the caller takes the TF32_BF16X2 route instead
+
+int split_operand_f16(tops_ctx* ctx, const void* src, int64_t rows, int64_t cols, Tmp& tmp, tops_ctx::SplitEntry* out) {
+    SplitScope* scope = ctx->split_scope;
+    if (scope)
+        for (auto& e : scope->entries)
+            if (e.src == src && e.rows == rows && e.cols == cols) { *out = e; return TOPS_OK; }
+    Tmp& holder = scope ? scope->keep : tmp;   // cached pairs live until the API call ends
+    const int64_t ld = (cols + 7) / 8 * 8;   // 16-byte aligned fp16 rows for every shape
+    int64_t pd[1] = {rows * ld}, sd[1] = {4};
+    tops_buf *hi = nullptr, *lo = nullptr, *sc = nullptr;
+    TRY(alloc_buf(ctx, TOPS_BF16, 1, pd, &hi)); holder.keep(hi);
+    TRY(alloc_buf(ctx, TOPS_BF16, 1, pd, &lo)); holder.keep(lo);
+    TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &sc)); holder.keep(sc);   // {scale, 1/scale, absmax bits, -}
+    unsigned* mx = reinterpret_cast<unsigned*>(sc->data) + 2;
+    CUDA_TRY(ctx, cudaMemsetAsync(mx, 0, 4, ctx->stream));
+    k::absmax_bits(lc_of(ctx), (const float*)src, rows * cols, mx);
+    k::split_f16_tensor_2d(lc_of(ctx), (const float*)src, rows, cols, ld, mx, hi->data, lo->data, (float*)sc->data);
+    TRY(check_launch(ctx, "split_f16"));
+    *out = tops_ctx::SplitEntry{src, rows, cols, hi->data, lo->data, ld, (float*)sc->data};
+    if (scope) scope->entries.push_back(*out);
+    return TOPS_OK;
+}
+
+int run_gemm(tops_ctx* ctx, GemmCall c);
+
+// fp32 operands under TOPS_PREC_F16X3: split both (cached per call) and run the fp16-pair kernel
+int run_gemm_f16x3(tops_ctx* ctx, const GemmCall& c0) {
+    if (c0.dtype != 0 || c0.io_bf16 || c0.M <= 0 || c0.N <= 0 || c0.K <= 0) return kF16X3Fallback;
+    const int64_t a_rows = c0.major_a == MAJOR_K ? c0.M : c0.K, a_cols = c0.major_a == MAJOR_K ? c0.K : c0.M;
+    const int64_t b_rows = c0.major_b == MAJOR_K ? c0.N : c0.K, b_cols = c0.major_b == MAJOR_K ? c0.K : c0.N;
+    if (c0.lda != a_cols || c0.ldb != b_cols) return kF16X3Fallback;   // strided views: not produced by this library
+    Tmp tmp;
+    tops_ctx::SplitEntry a, b;
+    TRY(split_operand_f16(ctx, c0.A, a_rows, a_cols, tmp, &a));
+    TRY(split_operand_f16(ctx, c0.B, b_rows, b_cols, tmp, &b));
+    int64_t sd[1] = {1};
+    tops_buf* sc = nullptr;
+    TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &sc)); tmp.keep(sc);
+    k::f16x3_pair_scale(lc_of(ctx), a.scale2, b.scale2, (float*)sc->data);
+    GemmCall c = c0;
+    c.dtype = 2; c.passes = 0;
+    c.A = a.hi; c.A2 = a.lo; c.lda = a.ld;
+    c.B = b.hi; c.B2 = b.lo; c.ldb = b.ld;
+    c.B16 = c.Blo16 = nullptr;
+    c.acc_scale_ptr = (const float*)sc->data;
+    if (c.chunk_kb <= 0) c.chunk_kb = c0.aux0 != nullptr ? ctx->f16x3_fwd_chunk_kb : ctx->f16x3_chunk_kb;
+    return run_gemm(ctx, c);
+}
+
 int run_gemm(tops_ctx* ctx, GemmCall c) {
     if (c.colsum_fused) *c.colsum_fused = 0;
     if (c.M <= 0 || c.N <= 0) return TOPS_OK;
-    const double es_in = c.dtype == 1 ? 2.0 : 4.0, es_out = c.io_bf16 ? 2.0 : 4.0;
+    if (c.dtype == 0 && ctx->precision == TOPS_PREC_F16X3) {   // fp32 operands become fp16 pairs; comes back here with dtype 2
+        const int r = run_gemm_f16x3(ctx, c);
+        if (r != kF16X3Fallback) return r;
+    }
+    const double es_in = c.dtype == 1 ? 2.0 : 4.0, es_out = c.io_bf16 ? 2.0 : 4.0;   // fp16 pairs: 2 x 2 bytes per element
     ProfScope prof_(ctx, c.tag ? c.tag : "gemm", 2.0 * c.M * c.N * (double)(c.K > 0 ? c.K : 0),
                     es_in * ((double)c.M * c.K + (double)c.N * c.K) + (c.epi == EPI_ATOMIC ? 4.0 : es_out) * (double)c.M * c.N * ((c.out1 ? 1 : 0) + (c.aux0 ? 1 : 0) + 1));
     if (c.epi == EPI_ATOMIC && !c.accumulate) {
@@ -196,14 +266,14 @@ int run_gemm(tops_ctx* ctx, GemmCall c) {
         if (c.epi == EPI_STORE || c.epi == EPI_ATOMIC) return TOPS_OK;
         return set_err(ctx, TOPS_ERR_SHAPE, "gemm: empty contraction dimension");
     }
-    const bool want_umma = c.dtype == 1 || ctx->precision != TOPS_PREC_FP32_SIMT;
+    const bool want_umma = c.dtype != 0 || ctx->precision != TOPS_PREC_FP32_SIMT;
     if (want_umma) {
-        c.passes = c.dtype != 0 ? 1 : ctx->precision == TOPS_PREC_TF32X3 ? 3 : ctx->precision == TOPS_PREC_TF32_BF16X2 ? 2 : 1;
+        c.passes = c.dtype != 0 ? 1 : ctx->precision == TOPS_PREC_TF32X3 ? 3 : (ctx->precision == TOPS_PREC_TF32_BF16X2 || ctx->precision == TOPS_PREC_F16X3) ? 2 : 1;
         char err[256];
         int r = gemm_umma_launch(c, ctx->stream, ctx->wd_dev, ctx->num_sms, err, sizeof err);
         if (r == 0) { ++ctx->launches; return TOPS_OK; }
         if (r > 0) return set_err(ctx, TOPS_ERR_CUDA, "%s", err);
-        if (c.dtype == 1) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "bf16 gemm needs 16-byte aligned operands with strides that are multiples of 8 elements (%s)", err);
+        if (c.dtype != 0) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "16-bit gemm needs 16-byte aligned operands with strides that are multiples of 8 elements (%s)", err);
     }
     if (c.out0_mc) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "the fused all-reduce needs the tcgen05 GEMM: 16-byte aligned operands and rows");
     int r = k::gemm_simt(lc_of(ctx), c);
@@ -260,6 +330,8 @@ extern "C" int tops_init(int device, tops_ctx** out) {
         return TOPS_ERR_CUDA;
     }
     memset(ctx->wd_host, 0, 64);
+    if (const char* e = getenv("TOPS_F16X3_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->f16x3_chunk_kb = v; }
+    if (const char* e = getenv("TOPS_F16X3_FWD_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->f16x3_fwd_chunk_kb = v; }
     *out = ctx;
     return TOPS_OK;
 }
@@ -288,7 +360,7 @@ extern "C" int tops_sync(tops_ctx* ctx) {
 extern "C" int tops_set_stream(tops_ctx* ctx, void* s) { CHECK_CTX(ctx); LOCK(ctx); ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return TOPS_OK; }
 extern "C" int tops_set_precision(tops_ctx* ctx, int p) {
     CHECK_CTX(ctx); LOCK(ctx);
-    if (p < 0 || p > 3) return set_err(ctx, TOPS_ERR_INVALID, "unknown precision %d", p);
+    if (p < 0 || p > 4) return set_err(ctx, TOPS_ERR_INVALID, "unknown precision %d", p);
     ctx->precision = p;
     return TOPS_OK;
 }
@@ -864,6 +936,109 @@ int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, 
     return TOPS_OK;
 }
 
+// ---- TOPS_PREC_F16X3: the whole forward + VJP of one layer on fp16 pairs, no operand split more than once.
+//   W  -> (W1, W2)  one scale sW for the tensor            (absmax + split: 2 small launches per call)
+//   X  -> (X1, X2)  one scale per sample row, rsX[s] = 1/scale; the same launch reduces max |dA|   (the only extra passes over HBM)
+//   forward GEMM    Z = acc * rsX[s] / sW + b, A = act(Z), dZ = dA * act'(A); its epilogue emits A (fp32), db (column sums of the
+//                   fp32 dZ) and dZ directly as the pair (dZ1, dZ2) of dZ * c * rsX[s] — fp32 dZ never exists in HBM
+//   dW GEMM         sum_s dZ'[s,o] X'[s,i] = c * dW: the per-sample factors cancel inside the contraction
+//   dX GEMM         dX[s,:] = acc / (c sW rsX[s])
+// c = 2^(13 - e(max|dA|)) / max_s rsX[s] keeps |dZ'| < 2^14 (|act'| <= 1).  All factors are powers of two: the scaling is exact.
+struct WPairF16 { void* w1 = nullptr; void* w2 = nullptr; float* s2 = nullptr; };
+
+bool f16x3_layer_ok(tops_ctx* ctx, const LayerShapes& s) {
+    return ctx->precision == TOPS_PREC_F16X3 && s.dtype == TOPS_F32 && s.B > 0 && s.i > 0 && s.o > 0 && (s.i % 8) == 0 && (s.o % 8) == 0;
+}
+
+int prep_wpair_f16(tops_ctx* ctx, const LayerShapes& s, const void* W, Tmp& tmp, WPairF16* out) {
+    int64_t pd[1] = {s.o * s.i}, sd[1] = {4};
+    tops_buf *hi = nullptr, *lo = nullptr, *sc = nullptr;
+    TRY(alloc_buf(ctx, TOPS_BF16, 1, pd, &hi)); tmp.keep(hi);
+    TRY(alloc_buf(ctx, TOPS_BF16, 1, pd, &lo)); tmp.keep(lo);
+    TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &sc)); tmp.keep(sc);
+    unsigned* mx = reinterpret_cast<unsigned*>(sc->data) + 2;
+    CUDA_TRY(ctx, cudaMemsetAsync(mx, 0, 4, ctx->stream));
+    ProfScope prof_(ctx, "split_f16_W", 0.0, 12.0 * (double)s.o * s.i);
+    k::absmax_bits(lc_of(ctx), (const float*)W, s.o * s.i, mx);
+    k::split_f16_tensor(lc_of(ctx), (const float*)W, s.o * s.i, mx, hi->data, lo->data, (float*)sc->data);
+    TRY(check_launch(ctx, "split_f16(W)"));
+    out->w1 = hi->data; out->w2 = lo->data; out->s2 = (float*)sc->data;
+    return TOPS_OK;
+}
+
+// X, dA, A, dX: device pointers to [B,i] / [B,o] fp32 row-major; dW [o,i], db [o] (nullable) fp32.  accumulate: dW/db are added to.
+int layer_fwd_grad_f16x3(tops_ctx* ctx, const LayerShapes& s, const void* X, const WPairF16& wp, const float* b, int act, const void* dA,
+                         void* A, void* dX, float* dW, float* db, bool accumulate, float* dW_mc) {
+    Tmp tmp;
+    int64_t xd[1] = {s.B * s.i}, zd[1] = {s.B * s.o}, rd[1] = {s.B}, sd[1] = {8};
+    tops_buf *x1 = nullptr, *x2 = nullptr, *z1 = nullptr, *z2 = nullptr, *rs = nullptr, *sc = nullptr;
+    TRY(alloc_buf(ctx, TOPS_BF16, 1, xd, &x1)); tmp.keep(x1);
+    TRY(alloc_buf(ctx, TOPS_BF16, 1, xd, &x2)); tmp.keep(x2);
+    TRY(alloc_buf(ctx, TOPS_BF16, 1, zd, &z1)); tmp.keep(z1);
+    TRY(alloc_buf(ctx, TOPS_BF16, 1, zd, &z2)); tmp.keep(z2);
+    TRY(alloc_buf(ctx, TOPS_F32, 1, rd, &rs)); tmp.keep(rs);
+    TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &sc)); tmp.keep(sc);   // [0..3] {1/sW, c, 1/c, 1/(c sW)}   [4] max rsX bits   [5] max|dA| bits
+    float* scal = (float*)sc->data;
+    unsigned* words = reinterpret_cast<unsigned*>(scal) + 4;
+    const float* rsX = (const float*)rs->data;
+    CUDA_TRY(ctx, cudaMemsetAsync(words, 0, 8, ctx->stream));
+    {
+        ProfScope prof_(ctx, "split_f16_X", 0.0, 8.0 * (double)s.B * s.i + 4.0 * (double)s.B * s.o);
+        k::split_f16_rows(lc_of(ctx), (const float*)X, s.B, s.i, x1->data, x2->data, (float*)rs->data, words, (const float*)dA, s.o, words + 1);
+        k::f16x3_layer_scales(lc_of(ctx), words, words + 1, wp.s2, scal);
+        TRY(check_launch(ctx, "split_f16(X)"));
+    }
+    // ---- forward: A, db, (dZ1, dZ2)
+    int db_fused = 0;
+    {
+        GemmCall g{};
+        g.dtype = 2; g.M = (int)s.B; g.N = (int)s.o; g.K = (int)s.i;
+        g.A = x1->data; g.A2 = x2->data; g.lda = s.i; g.major_a = MAJOR_K;
+        g.B = wp.w1; g.B2 = wp.w2; g.ldb = s.i; g.major_b = MAJOR_K;
+        g.epi = EPI_BIAS_ACT_DZ; g.act = act; g.alpha = 1.f; g.bias = b; g.tag = "gemm_fwd";
+        g.out0 = A; g.ld_out0 = s.o; g.aux0 = dA; g.ld_aux0 = s.o;
+        g.out1 = z1->data; g.out1b = z2->data; g.ld_out1 = s.o; g.out1_pair = 1; g.out1_scale_ptr = scal + 1; g.out1_row_scale = rsX;
+        g.acc_scale_ptr = scal + 0; g.row_scale = rsX; g.row_scale_inv = 0;
+        g.chunk_kb = ctx->f16x3_fwd_chunk_kb;
+        if (db) {
+            if (!accumulate) CUDA_TRY(ctx, cudaMemsetAsync(db, 0, sizeof(float) * (size_t)s.o, ctx->stream));
+            g.colsum = db; g.colsum_src = 2; g.colsum_fused = &db_fused;
+        }
+        TRY(run_gemm(ctx, g));
+        if (db && !db_fused) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "F16X3 layer: the staged epilogue was not available for db");
+    }
+    // ---- dW = dZ^T X (split-K over the batch)
+    {
+        GemmCall g{};
+        g.dtype = 2; g.M = (int)s.o; g.N = (int)s.i; g.K = (int)s.B;
+        g.A = z1->data; g.A2 = z2->data; g.lda = s.o; g.major_a = MAJOR_MN;
+        g.B = x1->data; g.B2 = x2->data; g.ldb = s.i; g.major_b = MAJOR_MN;
+        g.epi = EPI_ATOMIC; g.alpha = 1.f; g.out0 = dW; g.ld_out0 = s.i; g.tag = "gemm_dW"; g.accumulate = accumulate ? 1 : 0;
+        g.acc_scale_ptr = scal + 2; g.chunk_kb = ctx->f16x3_chunk_kb;
+        int* counters = nullptr;
+        if (dW_mc) {
+            const size_t n = ((size_t)(s.o + 127) / 128 + 1) * ((size_t)(s.i + 127) / 128 + 1) * 8 + 16;
+            CUDA_TRY(ctx, cudaMallocAsync((void**)&counters, n * sizeof(int), ctx->stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, n * sizeof(int), ctx->stream));
+            g.out0_mc = dW_mc; g.tile_counters = counters;
+        }
+        const int rc_ = run_gemm(ctx, g);
+        if (counters) cudaFreeAsync(counters, ctx->stream);
+        TRY(rc_);
+    }
+    // ---- dX = dZ W
+    if (dX) {
+        GemmCall g{};
+        g.dtype = 2; g.M = (int)s.B; g.N = (int)s.i; g.K = (int)s.o;
+        g.A = z1->data; g.A2 = z2->data; g.lda = s.o; g.major_a = MAJOR_K;
+        g.B = wp.w1; g.B2 = wp.w2; g.ldb = s.i; g.major_b = MAJOR_MN;
+        g.epi = EPI_STORE; g.alpha = 1.f; g.out0 = dX; g.ld_out0 = s.i; g.tag = "gemm_dX";
+        g.acc_scale_ptr = scal + 3; g.row_scale = rsX; g.row_scale_inv = 1; g.chunk_kb = ctx->f16x3_chunk_kb;
+        TRY(run_gemm(ctx, g));
+    }
+    return TOPS_OK;
+}
+
 int check_act(tops_ctx* ctx, int act) {
     if (act != TOPS_ACT_ID && act != TOPS_ACT_LOGISTIC) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "fflayer: activation %d is not fusable here (use tops_mlp_* for softmax)", act);
     return TOPS_OK;
@@ -890,7 +1065,14 @@ extern "C" int tops_fflayer_fwd_grad(tops_ctx* ctx, const tops_buf* X, const top
     if (dX) TRY(prep_out(ctx, dX, s.dtype, 2, dXs));
     TRY(prep_out(ctx, dW, TOPS_F32, 2, dWs));
     if (db) TRY(prep_out(ctx, db, TOPS_F32, 1, dbs));
-    Tmp tmp; tops_buf* dZ = nullptr;
+    Tmp tmp;
+    if (f16x3_layer_ok(ctx, s)) {
+        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp));
+        return layer_fwd_grad_f16x3(ctx, s, X->data, wp, b ? (const float*)b->data : nullptr, act, dA->data, (*A)->data, dX ? (*dX)->data : nullptr,
+                                    (float*)(*dW)->data, db ? (float*)(*db)->data : nullptr, false, nullptr);
+    }
+    SplitScope split_scope_(ctx);
+    tops_buf* dZ = nullptr;
     TRY(alloc_buf(ctx, s.dtype, 2, dAo, &dZ)); tmp.keep(dZ);
     WSplit ws; TRY(make_wsplit(ctx, W, tmp, &ws));
     int db_fused = 0;
@@ -914,6 +1096,7 @@ extern "C" int tops_fflayer_fwd_grad_host(tops_ctx* ctx, const float* X_host, co
     const int64_t o = W->dims[0], i = W->dims[1];
     int64_t dA_[2] = {B, o}, dX_[2] = {B, i}, g_[1] = {o * i + o};
     Tmp tmp;
+    SplitScope split_scope_(ctx);
     tops_buf *Xd = nullptr, *dAd = nullptr, *dZ = nullptr, *Ad = nullptr, *dXd = nullptr;
     TRY(alloc_buf(ctx, TOPS_F32, 2, dX_, &Xd)); tmp.keep(Xd);
     TRY(alloc_buf(ctx, TOPS_F32, 2, dA_, &dAd)); tmp.keep(dAd);
@@ -944,6 +1127,10 @@ extern "C" int tops_fflayer_fwd_grad_host(tops_ctx* ctx, const float* X_host, co
     }
     WSplit ws;
     int rc = make_wsplit(ctx, W, tmp, &ws);
+    const LayerShapes s_all{B, i, o, TOPS_F32};
+    const bool f16x3 = f16x3_layer_ok(ctx, s_all);
+    WPairF16 wp;
+    if (rc == TOPS_OK && f16x3) rc = prep_wpair_f16(ctx, s_all, W->data, tmp, &wp);
     int64_t r0 = 0;
     for (size_t c = 0; c < ev.size() && rc == TOPS_OK; ++c, r0 += rows_per) {
         const int64_t n = (B - r0 < rows_per) ? B - r0 : rows_per;
@@ -951,6 +1138,10 @@ extern "C" int tops_fflayer_fwd_grad_host(tops_ctx* ctx, const float* X_host, co
         LayerShapes s{n, i, o, TOPS_F32};
         const float* Xc = (const float*)Xd->data + r0 * i; const float* dAc = (const float*)dAd->data + r0 * o;
         float* Ac = (float*)Ad->data + r0 * o; float* dZc = (float*)dZ->data + r0 * o; float* dXc = (float*)dXd->data + r0 * i;
+        if (f16x3) {
+            rc = layer_fwd_grad_f16x3(ctx, s, Xc, wp, b ? (const float*)b->data : nullptr, act, dAc, Ac, dXc, dW, db, true, nullptr);
+            continue;
+        }
         int fused = 0;
         rc = fwd_gemm(ctx, s, Xc, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, Ac, dAc, dZc, nullptr, db, &fused, true, &ws);
         if (rc == TOPS_OK) rc = dw_db(ctx, s, dZc, Xc, dW, db, fused != 0, true);
@@ -985,7 +1176,14 @@ extern "C" int tops_fflayer_fwd_grad_mc(tops_ctx* ctx, const tops_buf* X, const 
     TRY(prep_out(ctx, grads_local, TOPS_F32, 1, g_));
     float* dW = (float*)(*grads_local)->data; float* db = dW + s.o * s.i;
     float* dW_mc = (float*)grads_mc; float* db_mc = dW_mc + s.o * s.i;
-    Tmp tmp; tops_buf* dZ = nullptr;
+    Tmp tmp;
+    if (f16x3_layer_ok(ctx, s)) {
+        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp));
+        TRY(layer_fwd_grad_f16x3(ctx, s, X->data, wp, b ? (const float*)b->data : nullptr, act, dA->data, (*A)->data, dX ? (*dX)->data : nullptr, dW, db, false, dW_mc));
+        k::mc_push(lc_of(ctx), db, db_mc, s.o);
+        return check_launch(ctx, "mc_push");
+    }
+    tops_buf* dZ = nullptr;
     TRY(alloc_buf(ctx, s.dtype, 2, dAo, &dZ)); tmp.keep(dZ);
     WSplit ws; TRY(make_wsplit(ctx, W, tmp, &ws));
     int db_fused = 0;
@@ -1014,6 +1212,7 @@ extern "C" int tops_fflayer_grad(tops_ctx* ctx, const tops_buf* X, const tops_bu
     TRY(prep_out(ctx, dW, TOPS_F32, 2, dWs));
     if (db) TRY(prep_out(ctx, db, TOPS_F32, 1, dbs));
     Tmp tmp; tops_buf* dZ = nullptr;
+    SplitScope split_scope_(ctx);
     TRY(alloc_buf(ctx, TOPS_F32, 2, dAo, &dZ)); tmp.keep(dZ);
     k::dact_mul(lc_of(ctx), act, (const float*)dA->data, (const float*)A_saved->data, (float*)dZ->data, dZ->numel);
     TRY(check_launch(ctx, "dact_mul"));
@@ -1060,6 +1259,7 @@ extern "C" int tops_mlp_fwd(tops_ctx* ctx, int n, const tops_buf* const* W, cons
     CHECK_CTX(ctx); LOCK(ctx);
     TRY(mlp_check(ctx, n, W, b, acts, X));
     Tmp tmp;
+    SplitScope split_scope_(ctx);   // F16X3: every tensor is split into its fp16 pair at most once per call
     const tops_buf* cur = X;
     for (int l = 0; l < n; ++l) {
         int64_t d[2] = {X->dims[0], W[l]->dims[0]};
@@ -1084,6 +1284,7 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
     if (!Y || Y->dtype != TOPS_F32 || Y->rank != 2 || Y->dims[0] != B || Y->dims[1] != o_last || Y->tr) return set_err(ctx, TOPS_ERR_SHAPE, "mlp: Y[B,o] fp32 expected");
     if (!dW || !db || !A_out || !loss_sum) return set_err(ctx, TOPS_ERR_INVALID, "mlp: NULL output slot");
     Tmp tmp;
+    SplitScope split_scope_(ctx);   // F16X3: every tensor (activations, dZ, W) is split into its fp16 pair at most once per call
     std::vector<const tops_buf*> acts_in(n);     // input of layer l
     std::vector<tops_buf*> Zs(n, nullptr);
     TRY(prep_out(ctx, loss_sum, TOPS_F32, 0, nullptr));

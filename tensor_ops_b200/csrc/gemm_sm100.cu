@@ -34,7 +34,7 @@ enum Swz { SWZ_128 = 0, SWZ_128_ATOM32 = 1, SWZ_64 = 2 };
 bool make_map(CUtensorMap* m, int dtype, const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, int swz) {
     auto enc = get_encode();
     if (!enc) return false;
-    const size_t es = dtype == 1 ? 2 : 4;
+    const size_t es = dtype == 0 ? 4 : 2;   // 0 fp32, 1 bf16, 2 fp16
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return false;
     if (((size_t)ld * es) % 16 != 0) return false;
     if (inner <= 0 || outer <= 0) return false;
@@ -42,7 +42,7 @@ bool make_map(CUtensorMap* m, int dtype, const void* ptr, long long inner, long 
     cuuint64_t strides[1] = {(cuuint64_t)ld * es};
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+    CUresult r = enc(m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                      const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz == SWZ_128_ATOM32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swz == SWZ_64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -75,8 +75,10 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     };
     if (c.M <= 0 || c.N <= 0 || c.K <= 0) return fail(-1, "gemm: empty problem");
     if (c.passes >= 2 && c.dtype != 0) return fail(-1, "gemm: the split modes need fp32 operands");
-    int passes = c.passes >= 2 ? c.passes : 1;
-    const int es = c.dtype == 1 ? 2 : 4;
+    if (c.dtype == 2 && (!c.A2 || !c.B2)) return fail(-1, "gemm: fp16-pair operands need both planes");
+    if (c.dtype == 2 && c.io_bf16) return fail(-1, "gemm: the fp16-pair mode writes fp32 outputs");
+    int passes = c.dtype == 2 ? 4 : c.dtype == 1 ? 1 : c.passes >= 2 && c.passes <= 3 ? c.passes : 1;
+    const int es = c.dtype == 0 ? 4 : 2;
     const int kb_elems = 128 / es;
     int bn = c.block_n;
     if (bn == 0) bn = (c.N <= 128) ? 128 : 256;
@@ -97,6 +99,15 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     if (c.major_b == MAJOR_K) ok = make_map(&tb, c.dtype, c.B, c.K, c.N, c.ldb, kb_elems, bn / cg, SWZ_128);
     else ok = make_map(&tb, c.dtype, c.B, c.N, c.K, c.ldb, kb_elems, kb_elems, c.dtype == 0 ? SWZ_128_ATOM32 : SWZ_128);
     if (!ok) return fail(-1, "gemm: operand B not expressible as a TMA tensor map (alignment/stride)");
+    if (c.dtype == 2) {   // lo planes: same geometry as the hi planes, delivered into the second half of every stage
+        if (c.major_a == MAJOR_K) ok = make_map(&tm[3], 2, c.A2, c.K, c.M, c.lda, kb_elems, 128, SWZ_128);
+        else ok = make_map(&tm[3], 2, c.A2, c.M, c.K, c.lda, kb_elems, kb_elems, SWZ_128);
+        if (ok) {
+            if (c.major_b == MAJOR_K) ok = make_map(&tm[4], 2, c.B2, c.K, c.N, c.ldb, kb_elems, bn / cg, SWZ_128);
+            else ok = make_map(&tm[4], 2, c.B2, c.N, c.K, c.ldb, kb_elems, kb_elems, SWZ_128);
+        }
+        if (!ok) return fail(-1, "gemm: lo planes not expressible as TMA tensor maps (alignment/stride)");
+    }
     // Staged epilogue: outputs are transposed through shared memory and written with coalesced 16-byte stores, the aux operand
     // (if any) is fetched by TMA as 32 x 32 boxes (fp32: 128-byte rows, SWIZZLE_128B; bf16: 64-byte rows, SWIZZLE_64B).
     // Needs 16-byte aligned rows everywhere; otherwise the kernel falls back to its direct register<->global epilogue.
@@ -106,9 +117,14 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
         auto aligned = [&](const void* ptr, long long ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((size_t)ld * oes) % 16 == 0; };
         const bool has_out1 = c.epi == EPI_BIAS_ACT_DZ || c.epi == EPI_BIAS_ACT_SE;
         const bool has_aux = has_out1 || c.epi == EPI_MUL_DACT || (c.epi == EPI_STORE && c.aux0 != nullptr);
-        tma_epi = aligned(c.out0, c.ld_out0) && (!has_out1 || aligned(c.out1, c.ld_out1));
+        tma_epi = aligned(c.out0, c.ld_out0);
+        if (tma_epi && has_out1 && c.out1_pair)   // fp16 planes: 16-byte aligned rows of 2-byte elements
+            tma_epi = c.out1b && (reinterpret_cast<uintptr_t>(c.out1) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.out1b) & 15) == 0 && ((size_t)c.ld_out1 * 2) % 16 == 0;
+        else if (tma_epi && has_out1) tma_epi = aligned(c.out1, c.ld_out1);
         if (tma_epi && has_aux) tma_epi = make_map(&tm[2], c.io_bf16 ? 1 : 0, c.aux0, c.N, c.M, c.ld_aux0, 32, 32, c.io_bf16 ? SWZ_64 : SWZ_128);
     }
+    if (c.out1_pair && !tma_epi) return fail(-1, "gemm: the fp16-pair output needs the staged epilogue (16-byte aligned rows)");
+    if ((c.acc_scale_ptr || c.row_scale || c.out1_pair) && passes < 2) return fail(-1, "gemm: accumulator scaling / pair output exist in the chunked kernels only");
     // passes == 2 with a pre-split B: two more maps delivering the bf16 tiles in the layouts the splitter would have produced
     // (K-major: 64-byte rows, SWIZZLE_64B; MN-major: [32 k-rows x 64 elements], SWIZZLE_128B)
     bool b_presplit = false;
@@ -140,7 +156,10 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     p.split_k = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
     // 3-pass: TMEM accumulation truncates (~2e-8 relative per MMA, linear in the chain length), so a chunk of
     // chunk_kb k-blocks (12 MMAs each) is promoted to round-to-nearest fp32 register sums; 4 k-blocks = 128 K-elements.
-    p.chunk_kb = c.chunk_kb > 0 ? c.chunk_kb : 4;
+    // F16X3: k-blocks hold 64 K-elements and 12 MMAs; 2 k-blocks = 128 K-elements = 24 MMAs per chunk.
+    p.chunk_kb = c.chunk_kb > 0 ? c.chunk_kb : (c.dtype == 2 ? 2 : 4);
+    p.acc_scale_ptr = c.acc_scale_ptr; p.row_scale = c.row_scale; p.row_scale_inv = c.row_scale_inv;
+    p.out1_pair = c.out1_pair; p.out1b = c.out1b; p.out1_scale_ptr = c.out1_scale_ptr; p.out1_row_scale = c.out1_row_scale;
     p.epi = c.epi; p.act = c.act; p.alpha = c.alpha; p.beta = c.beta;
     p.out0 = c.out0; p.ld_out0 = c.ld_out0;
     p.out1 = c.out1; p.ld_out1 = c.ld_out1;

@@ -31,6 +31,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <type_traits>
 
@@ -74,6 +75,17 @@ struct GemmParams {
     int vec_ok;               // 16-byte vector access legal for out0/out1/aux0
     int b_presplit;           // PASSES == 2: bf16(B) and bf16(B_lo) exist in HBM (tmB16 / tmBlo16): TMA loads them, the splitter handles A only
     int tma_epi;              // staged epilogue: outputs via smem staging + coalesced stores, aux operand by TMA (tmAux valid if needed)
+    // Chunked kernels: the register accumulators are multiplied by (*acc_scale_ptr) * row_scale[m] (or / row_scale[m]) before the
+    // epilogue math.  F16X3 operands are stored scaled by powers of two; these factors undo the scaling exactly.
+    const float* acc_scale_ptr;   // device scalar, NULL = 1
+    const float* row_scale;       // [M], NULL = 1
+    int row_scale_inv;            // 1: divide by row_scale[m] instead of multiplying
+    // out1 written as an fp16 PAIR (staged fp32 epilogues only): t = out1 * (*out1_scale_ptr) * out1_row_scale[m];
+    // out1 <- fp16(t), out1b <- fp16(t - fp16(t)); ld_out1 counts fp16 elements.  The column sums (colsum_src = 2) use the fp32 values.
+    int out1_pair;
+    void* out1b;
+    const float* out1_scale_ptr;  // device scalar, NULL = 1
+    const float* out1_row_scale;  // [M], NULL = 1
     unsigned int* watchdog;   // mapped host memory, 2 words
 };
 
@@ -89,8 +101,13 @@ struct GemmCfg {
     static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
     // split modes keep a second set of tiles per stage: PASSES == 3 the fp32 lo tiles (RAW_BYTES); PASSES == 2 four bf16 tiles
     // (bf16(A), bf16(A_lo), bf16(B), bf16(B_lo)), half the bytes each — RAW_BYTES in total as well
+    // PASSES == 4 (F16X3): fp16 operands pre-split in HBM into (hi, lo) planes, both delivered by TMA — 3 MMA passes
+    // hi*hi + lo*hi + hi*lo like PASSES == 3, but no splitter warps and fp16 tensor-core rate
+    static constexpr bool PRESPLIT = PASSES == 4;
+    static constexpr int NPASS = PRESPLIT ? 3 : PASSES;
+    static constexpr int IO_BYTES = PRESPLIT ? 4 : (int)sizeof(T);   // element size of out0 / out1 / aux0
     static constexpr int STAGE_BYTES = RAW_BYTES * (PASSES >= 2 ? 2 : 1);
-    static constexpr int NUM_THREADS = PASSES >= 2 ? 512 : 384;
+    static constexpr int NUM_THREADS = (PASSES == 2 || PASSES == 3) ? 512 : 384;
     static constexpr int EPI_THREADS = 256;                 // 8 epilogue warps: 2 per TMEM lane quarter, each owning half of the tile's columns
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = 512;
@@ -98,7 +115,7 @@ struct GemmCfg {
     // 1-pass: one block for the aux operand (prefetched one chunk ahead) + one for outputs; 3-pass: one shared block.
     static constexpr int EPI_WARPS = EPI_THREADS / 32;
     static constexpr int EPI_W = 32;                                       // columns per epilogue block
-    static constexpr int EPI_BLOCK_BYTES = 32 * EPI_W * (int)sizeof(T);    // 4096 (fp32, 128-byte rows) / 2048 (bf16, 64-byte rows)
+    static constexpr int EPI_BLOCK_BYTES = 32 * EPI_W * IO_BYTES;          // 4096 (fp32, 128-byte rows) / 2048 (bf16, 64-byte rows)
     // two blocks per warp (aux operand prefetched while the previous block is written out) when the pipeline stages leave
     // room for them, otherwise one block shared by the aux operand and the outputs
     static constexpr int EPI_NBUF = (232448 - STAGES * STAGE_BYTES - 2048 >= EPI_WARPS * 2 * EPI_BLOCK_BYTES) ? 2 : 1;
@@ -107,7 +124,8 @@ struct GemmCfg {
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + EPI_BYTES + 1024 /*alignment slack*/;
     static_assert(BAR_BYTES <= 1024 && (3 * STAGES + 4 + EPI_WARPS) * 8 + 4 <= BAR_BYTES, "barrier area");
-    static_assert(PASSES == 1 || (PASSES >= 2 && PASSES <= 3 && sizeof(T) == 4), "the hi/lo split modes are fp32 techniques");
+    static_assert(PASSES == 1 || (PASSES >= 2 && PASSES <= 3 && sizeof(T) == 4) || (PASSES == 4 && std::is_same<T, __half>::value),
+                  "in-kernel hi/lo split modes take fp32 operands; the pre-split mode takes fp16 pairs");
     static_assert(BN == 128 || BN == 256, "BN");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -321,6 +339,27 @@ __device__ __forceinline__ void stage_write_row(uint32_t buf, int r, const float
         ptx::sts128(buf + stage_off<ROWB>(r, j), u);
     }
 }
+// One row of W fp32 values -> an fp16 PAIR: t = x * s; hi = fp16(t), lo = fp16(t - hi)  (t - hi is exact in fp32).
+// The two planes are staged as 32 x W fp16 blocks (64-byte rows, SWIZZLE_64B layout) at `buf` and `buf + 32 * W * 2`.
+template <int W>
+__device__ __forceinline__ void stage_write_row_f16pair(uint32_t buf, int r, const float (&x)[W], float s) {
+    static_assert(W == 32, "64-byte fp16 rows");
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 uh, ul;
+        __half2* hh = reinterpret_cast<__half2*>(&uh);
+        __half2* hl = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float t0 = x[j * 8 + e * 2] * s, t1 = x[j * 8 + e * 2 + 1] * s;
+            hh[e] = __floats2half2_rn(t0, t1);
+            const float2 hf = __half22float2(hh[e]);
+            hl[e] = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
+        }
+        ptx::sts128(buf + stage_off<64>(r, j), uh);
+        ptx::sts128(buf + 32 * W * 2 + stage_off<64>(r, j), ul);
+    }
+}
 // Column sums of a staged 32 x W block, added into colsum[col .. col+W) with one red per column (db = sum_s dZ[s,:]).
 template <typename IO, int W>
 __device__ __forceinline__ void stage_colsum(uint32_t buf, int lane, int col, int N, float* colsum) {
@@ -422,6 +461,7 @@ struct EpiWarp {
     uint64_t* aux_bar;     // mbarrier the aux TMA load completes on
     uint32_t consumed;     // aux loads consumed so far (parity of the next wait)
     bool in_flight;        // the aux block of the block about to be processed has already been requested
+    float out1_s;          // out1_pair: this lane's (row's) scale for the fp16 pair of out1
 };
 
 template <typename IO, int W>
@@ -457,6 +497,22 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, const CUtensorMap
     if (p.colsum != nullptr && p.colsum_src == 1) stage_colsum<IO, W>(w.out_buf, lane, col, p.N, p.colsum);
     __syncwarp();
     if (has_out1) {
+        if constexpr (std::is_same<IO, float>::value && W == 32) {
+            if (p.out1_pair) {   // out1 leaves as an fp16 pair (operand of the next F16X3 GEMMs); its column sums come from the fp32 values
+                if (p.colsum != nullptr && p.colsum_src == 2) {
+                    stage_write_row<IO, W>(w.out_buf, lane, x);
+                    __syncwarp();
+                    stage_colsum<IO, W>(w.out_buf, lane, col, p.N, p.colsum);
+                    __syncwarp();
+                }
+                stage_write_row_f16pair<W>(w.out_buf, lane, x, w.out1_s);
+                __syncwarp();
+                stage_store_global<__half, W>(w.out_buf, lane, p.out1, p.ld_out1, row0, col, p.M, p.N);
+                stage_store_global<__half, W>(w.out_buf + 32 * W * 2, lane, p.out1b, p.ld_out1, row0, col, p.M, p.N);
+                __syncwarp();
+                return;
+            }
+        }
         stage_write_row<IO, W>(w.out_buf, lane, x);
         __syncwarp();
         stage_store_global<IO, W>(w.out_buf, lane, p.out1, p.ld_out1, row0, col, p.M, p.N);
@@ -496,7 +552,11 @@ __global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>::N
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAux,
                  const __grid_constant__ CUtensorMap tmB16, const __grid_constant__ CUtensorMap tmBlo16, const GemmParams p) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
-    constexpr bool kBF16 = sizeof(T) == 2;
+    constexpr bool kBF16 = sizeof(T) == 2;   // 16-bit operands (bf16 or fp16): kind::f16, K = 16 per instruction
+    constexpr uint32_t kFmt = std::is_same<T, __half>::value ? 0u : (kBF16 ? 1u : 2u);   // instruction-descriptor operand format
+    constexpr bool kPresplit = PASSES == 4;  // F16X3: (hi, lo) fp16 planes of both operands arrive by TMA (maps tmB16 / tmBlo16 = A_lo / B_lo)
+    constexpr int NPASS = Cfg::NPASS;
+    constexpr bool kSplitter = PASSES == 2 || PASSES == 3;
     constexpr bool kChunked = PASSES >= 2;   // TMEM holds one chunk; the running sum lives in epilogue registers
     constexpr int BM = Cfg::BM;
     constexpr int KB = Cfg::KB_ELEMS;
@@ -528,7 +588,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
         if (p.tma_epi && epi_has_aux(p)) ptx::prefetch_tensormap(&tmAux);
-        if (PASSES == 2 && p.b_presplit) { ptx::prefetch_tensormap(&tmB16); ptx::prefetch_tensormap(&tmBlo16); }
+        if ((PASSES == 2 && p.b_presplit) || kPresplit) { ptx::prefetch_tensormap(&tmB16); ptx::prefetch_tensormap(&tmBlo16); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -536,7 +596,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::mbar_init(&empty_bar[s], 1);
             // ready: CG = 1: the 128 splitter threads (3-pass).  CG = 2: splitter threads of both CTAs (3-pass) or the two
             // relay threads that forward "my TMA data has landed" to the leader (1-pass)
-            ptx::mbar_init(&ready_bar[s], CG == 1 ? 128 : (PASSES >= 2 ? 256 : 2));
+            ptx::mbar_init(&ready_bar[s], CG == 1 ? 128 : (kSplitter ? 256 : 2));
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full[a], 1);
@@ -574,22 +634,32 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if constexpr (CG == 2) ptx::mbar_wait_cluster(&empty_bar[s], ph ^ 1, wd, 0x100 + s);
                     else ptx::mbar_wait(&empty_bar[s], ph ^ 1, wd, 0x100 + s);
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::RAW_BYTES + ((PASSES == 2 && p.b_presplit) ? Cfg::B_BYTES : 0));
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], kPresplit ? 2 * Cfg::RAW_BYTES : Cfg::RAW_BYTES + ((PASSES == 2 && p.b_presplit) ? Cfg::B_BYTES : 0));
                     uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
-                    if constexpr (MA == MAJOR_K) {
-                        ptx::tma_load_2d(sa, &tmA, &full_bar[s], kb * KB, m0);
-                    } else {
+                    auto load_a = [&](uint8_t* dst, const CUtensorMap* map) {
+                        if constexpr (MA == MAJOR_K) {
+                            ptx::tma_load_2d(dst, map, &full_bar[s], kb * KB, m0);
+                        } else {
 #pragma unroll
-                        for (int r = 0; r < BM / KB; ++r)
-                            ptx::tma_load_2d(sa + r * (KB * 128), &tmA, &full_bar[s], m0 + r * KB, kb * KB);
-                    }
-                    if constexpr (MB == MAJOR_K) {
-                        ptx::tma_load_2d(sb, &tmB, &full_bar[s], kb * KB, n0);
-                    } else {
+                            for (int r = 0; r < BM / KB; ++r)
+                                ptx::tma_load_2d(dst + r * (KB * 128), map, &full_bar[s], m0 + r * KB, kb * KB);
+                        }
+                    };
+                    auto load_b = [&](uint8_t* dst, const CUtensorMap* map) {
+                        if constexpr (MB == MAJOR_K) {
+                            ptx::tma_load_2d(dst, map, &full_bar[s], kb * KB, n0);
+                        } else {
 #pragma unroll
-                        for (int r = 0; r < (BN / CG) / KB; ++r)
-                            ptx::tma_load_2d(sb + r * (KB * 128), &tmB, &full_bar[s], n0 + r * KB, kb * KB);
+                            for (int r = 0; r < (BN / CG) / KB; ++r)
+                                ptx::tma_load_2d(dst + r * (KB * 128), map, &full_bar[s], n0 + r * KB, kb * KB);
+                        }
+                    };
+                    load_a(sa, &tmA);
+                    load_b(sb, &tmB);
+                    if constexpr (kPresplit) {   // the lo planes land where the 3-pass splitter would have written its lo tiles
+                        load_a(sa + Cfg::RAW_BYTES, &tmB16);
+                        load_b(sb + Cfg::RAW_BYTES, &tmBlo16);
                     }
                     if constexpr (PASSES == 2) {
                         if (p.b_presplit) {   // the small operand was split once in HBM: its bf16 tiles arrive ready-made
@@ -612,7 +682,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         } else if (warp == 1 && lane == 0 && leader) {
             // ===================================================== MMA issuer (CG = 2: the leader CTA issues for the pair)
-            constexpr uint32_t idesc = ptx::make_idesc(kBF16 ? 1u : 2u, MA == MAJOR_MN, MB == MAJOR_MN, BM * CG, BN);
+            constexpr uint32_t idesc = ptx::make_idesc(kFmt, MA == MAJOR_MN, MB == MAJOR_MN, BM * CG, BN);
             // byte advance of the descriptor start address per UMMA_K step, and the LBO/SBO of each layout
             constexpr uint32_t a_step = (MA == MAJOR_K) ? 32u : (uint32_t)Cfg::UMMA_K * 128u;
             constexpr uint32_t b_step = (MB == MAJOR_K) ? 32u : (uint32_t)Cfg::UMMA_K * 128u;
@@ -678,7 +748,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             }
                         } else {
 #pragma unroll
-                        for (int pass = 0; pass < PASSES; ++pass) {
+                        for (int pass = 0; pass < NPASS; ++pass) {
                             // pass 0: A_hi*B_hi   pass 1: A_lo*B_hi   pass 2: A_hi*B_lo
                             // pass 0 needs only the raw tiles, so it is issued as soon as the TMA data lands and runs on the
                             // tensor pipe while the splitter warps are still producing the lo tiles for passes 1 and 2
@@ -711,7 +781,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     else ptx::umma_commit(&tmem_full[acc]);
                 }
             }
-        } else if (CG == 2 && PASSES == 1 && warp == 3 && lane == 0) {
+        } else if (CG == 2 && !kSplitter && warp == 3 && lane == 0) {
             // ===================================================== relay (CTA pair, 1-pass): forward "my stage has landed" to the leader
             const uint32_t ready0 = ptx::mapa(ptx::smem_u32(&ready_bar[0]), 0);
             int s = 0; uint32_t ph = 0;
@@ -738,7 +808,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         EpiWarp ew;
         ew.aux_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
         ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * Cfg::EPI_BLOCK_BYTES;
-        ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false;
+        ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false; ew.out1_s = 1.0f;
         const uint32_t tmem_empty0 = CG == 2 ? ptx::mapa(ptx::smem_u32(&tmem_empty[0]), 0) : 0u;   // the leader's accumulator-free barriers
         int it = 0;
         float loss_acc = 0.f;
@@ -783,7 +853,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp < kSplitWarp0) {
         // ===================================================== epilogue, 3-pass: warps 4-11, chunked promotion to registers
-        ptx::setmaxnreg_inc<208>();
+        if constexpr (kSplitter) ptx::setmaxnreg_inc<208>();   // 512 threads: 128 regs each at launch, 8 non-epilogue warps give 80 each
+        else ptx::setmaxnreg_inc<224>();                        // 384 threads: 168 at launch, 4 non-epilogue warps give 120 each
         constexpr int HC = BN / 2;            // columns per warp: half of the tile
         const int q = warp & 3;               // TMEM lane quarter (hardware rule: warp w reads lanes 32*(w%4)..+31)
         const int half = (warp - 4) >> 2;     // column half
@@ -792,7 +863,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         EpiWarp ew;
         ew.aux_buf = ptx::smem_u32(epi_smem + (warp - 4) * Cfg::EPI_WARP_BYTES);
         ew.out_buf = ew.aux_buf + (Cfg::EPI_NBUF - 1) * Cfg::EPI_BLOCK_BYTES;
-        ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false;
+        ew.aux_bar = &epi_bar[warp - 4]; ew.consumed = 0; ew.in_flight = false; ew.out1_s = 1.0f;
         const uint32_t tmem_empty0 = CG == 2 ? ptx::mapa(ptx::smem_u32(&tmem_empty[0]), 0) : 0u;   // the leader's accumulator-free barriers
         int it = 0;
         float loss_acc = 0.f;
@@ -829,6 +900,19 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
+            if (p.acc_scale_ptr != nullptr || p.row_scale != nullptr) {   // undo the power-of-two operand scaling (exact)
+                float rs = p.acc_scale_ptr != nullptr ? __ldg(p.acc_scale_ptr) : 1.0f;
+                if (p.row_scale != nullptr && row < p.M) {
+                    const float r = __ldg(p.row_scale + row);
+                    rs *= p.row_scale_inv ? __frcp_rn(r) : r;   // powers of two: exact
+                }
+#pragma unroll
+                for (int e = 0; e < HC; ++e) sum[e] *= rs;
+            }
+            if (p.out1_pair) {
+                ew.out1_s = p.out1_scale_ptr != nullptr ? __ldg(p.out1_scale_ptr) : 1.0f;
+                if (p.out1_row_scale != nullptr && row < p.M) ew.out1_s *= __ldg(p.out1_row_scale + row);
+            }
             if (row0 < p.M) {
                 // ONE copy of the block code (the fused epilogue is large; unrolled four times it thrashes the instruction
                 // cache): always process sum[0..31], then rotate the register accumulators down by one block.
@@ -852,7 +936,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
             if (lane == 0) atomicAdd(p.loss, loss_acc);
         }
-    } else {
+    } else if constexpr (kSplitter) {
         // ===================================================== hi/lo splitter (3xTF32): warps 12-15
         ptx::setmaxnreg_dec<48>();
         const int t = threadIdx.x - kSplitWarp0 * 32;   // 0..127

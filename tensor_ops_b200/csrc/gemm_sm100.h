@@ -7,12 +7,20 @@
 namespace tops {
 
 struct GemmCall {
-    int dtype;      // 0 = fp32 operands (TF32 tensor cores), 1 = bf16 operands
-    int passes;     // 1 = single TF32/bf16 pass, 3 = 3xTF32 hi/lo split (fp32-grade accuracy)
+    int dtype;      // 0 = fp32 operands (TF32 tensor cores), 1 = bf16 operands, 2 = fp16 PAIRS (F16X3: A/B = hi planes, A2/B2 = lo planes,
+                    //     lda/ldb in fp16 elements; three fp16 passes hi*hi + lo*hi + hi*lo, fp32 accumulate; outputs / aux are fp32)
+    int passes;     // dtype 0: 1 = single TF32 pass, 2 = TF32 + two bf16 correction passes, 3 = 3xTF32 hi/lo split; ignored otherwise
     int M, N, K;
     const void* A; long long lda; int major_a;   // 0: A stored [M,K] (K contiguous), 1: stored [K,M]
     const void* B; long long ldb; int major_b;   // 0: B stored [N,K] (K contiguous), 1: stored [K,N]
     const void* B16; const void* Blo16;   // optional (passes == 2): bf16(B) and bf16(B - trunc_tf32(B)), same shape / ldb as B, pre-split in HBM
+    const void* A2; const void* B2;       // dtype 2: the lo planes (same shape / leading dimension as A / B)
+    // dtype 2: the operands were scaled by powers of two when they were split; the accumulators are multiplied by
+    // (*acc_scale_ptr) * row_scale[m] (or / row_scale[m]) before the epilogue math (all factors powers of two: exact)
+    const float* acc_scale_ptr;           // device scalar, NULL = 1
+    const float* row_scale; int row_scale_inv;   // [M] device vector, NULL = 1
+    // out1 as an fp16 pair for the next F16X3 GEMM: t = out1 * (*out1_scale_ptr) * out1_row_scale[m]; out1 <- fp16(t), out1b <- fp16(t - fp16(t))
+    int out1_pair; void* out1b; const float* out1_scale_ptr; const float* out1_row_scale;
     int epi, act;
     float alpha, beta;
     void* out0; long long ld_out0;

@@ -50,9 +50,13 @@ cudaError_t launch_cg(int bn, int passes, const CUtensorMap* tm, const GemmParam
         // fp32 1-pass: one stage fewer than fits, so that each epilogue warp gets separate aux and output staging blocks
         if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 6 : 5, 1, CG>(tm, p, grid, st);
         return launch_one<T, MA, MB, 256, CG == 2 ? 5 : 3, 1, CG>(tm, p, grid, st);
+    } else if constexpr (std::is_same<T, __half>::value) {   // F16X3: (hi, lo) planes of both operands per stage: 2 * (128 + bn/CG) * 128 bytes
+        if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 4 : 3, 4, CG>(tm, p, grid, st);
+        return launch_one<T, MA, MB, 256, CG == 2 ? 3 : 2, 4, CG>(tm, p, grid, st);
+    } else {
+        if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 8 : 6, 1, CG>(tm, p, grid, st);
+        return launch_one<T, MA, MB, 256, CG == 2 ? 6 : 4, 1, CG>(tm, p, grid, st);
     }
-    if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 8 : 6, 1, CG>(tm, p, grid, st);
-    return launch_one<T, MA, MB, 256, CG == 2 ? 6 : 4, 1, CG>(tm, p, grid, st);
 }
 
 template <typename T, int MA, int MB>
@@ -61,10 +65,11 @@ cudaError_t launch_major(int cg, int bn, int passes, const CUtensorMap* tm, cons
     return launch_cg<T, MA, MB, 1>(bn, passes, tm, p, grid, st);
 }
 
-// one entry per (A layout, B layout); dtype 0 = fp32 operands, 1 = bf16
+// one entry per (A layout, B layout); dtype 0 = fp32 operands, 1 = bf16, 2 = fp16 pairs (F16X3)
 #define TOPS_DEFINE_GEMM_VARIANT(NAME, MA, MB)                                                                                          \
     cudaError_t NAME(int dtype, int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {    \
         if (dtype == 1) return launch_major<__nv_bfloat16, MA, MB>(cg, bn, 1, tm, p, grid, st);                                        \
+        if (dtype == 2) return launch_major<__half, MA, MB>(cg, bn, 4, tm, p, grid, st);                                               \
         return launch_major<float, MA, MB>(cg, bn, passes, tm, p, grid, st);                                                           \
     }
 

@@ -27,6 +27,22 @@ void cast_bf16_f32(const LaunchCtx&, const void* s, float* d, int64_t n);
 void split_bf16(const LaunchCtx&, const float* x, void* v, void* lo, int64_t n);
 void eye(const LaunchCtx&, float* p, int64_t n);
 
+// ---- F16X3 operand preparation (split_f16.cu): x -> fp16 pair (hi, lo) of x * 2^k, see the header of that file
+// max |x| as fp32 bits, atomicMax into the PRE-ZEROED word out_bits
+void absmax_bits(const LaunchCtx&, const float* x, int64_t n, unsigned* out_bits);
+// one scale for the whole tensor, taken from absmax_bits (device); scale2 (nullable) receives {scale, 1/scale}
+void split_f16_tensor(const LaunchCtx&, const float* x, int64_t n, const unsigned* absmax_bits_dev, void* hi, void* lo, float* scale2);
+// the same for a [rows, cols] matrix with fp16 planes of leading dimension ld_out >= cols (padding never read)
+void split_f16_tensor_2d(const LaunchCtx&, const float* x, int64_t rows, int64_t cols, int64_t ld_out, const unsigned* absmax_bits_dev, void* hi, void* lo, float* scale2);
+// out[0] = 1 / (sA * sB) from two {scale, 1/scale} records
+void f16x3_pair_scale(const LaunchCtx&, const float* sa2, const float* sb2, float* out);
+// one scale per row: rs[r] = 1/scale_r; max_rs_bits (PRE-ZEROED) = max_r rs[r] as fp32 bits.  y (nullable, [rows, ycols]):
+// max |y| is reduced into the PRE-ZEROED ymax_bits by the same launch
+void split_f16_rows(const LaunchCtx&, const float* x, int64_t rows, int64_t cols, void* hi, void* lo, float* rs, unsigned* max_rs_bits,
+                    const float* y, int64_t ycols, unsigned* ymax_bits);
+// out4 = {1/sW, c, 1/c, 1/(c sW)}: the device scalars of one F16X3 ffLayer forward + VJP (sW2 = {sW, 1/sW}, nullable)
+void f16x3_layer_scales(const LaunchCtx&, const unsigned* max_rs_bits, const unsigned* absmax_dA_bits, const float* sW2, float* out4);
+
 // ---- elementwise
 void axpy(const LaunchCtx&, float alpha, const float* x, const float* y /*nullable*/, float* out, int64_t n);
 void add_n(const LaunchCtx&, int n_in, const float* const* xs, float* out, int64_t n);   // left fold, n_in <= 8

@@ -2,7 +2,7 @@
 and the committed golden fixtures.
 
 Tolerances (fp32 device vs fp64 oracle), norm-wise  ||dev - ref||_F / ||ref||_F  per output tensor:
-    TOPS_PREC_TF32_BF16X2 (default), TOPS_PREC_TF32X3 and TOPS_PREC_FP32_SIMT : 1e-5   (BASELINE.json north_star: "within 1e-5 relative fp32")
+    TOPS_PREC_F16X3 (default), TOPS_PREC_TF32_BF16X2, TOPS_PREC_TF32X3 and TOPS_PREC_FP32_SIMT : 1e-5   (BASELINE.json north_star: "within 1e-5 relative fp32")
     TOPS_PREC_TF32 (throughput mode, 10-bit mantissa)  : 3e-3   (NOT a parity mode; checked so it cannot silently rot)
     bf16 storage + fp32 accumulate                     : 2e-2 against the oracle run on bf16-rounded inputs
 """
@@ -20,15 +20,16 @@ from tensor_ops_b200.batched import BatchT
 pytestmark = pytest.mark.gpu
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL = {tb.PREC_TF32_BF16X2: 1e-5, tb.PREC_TF32X3: 1e-5, tb.PREC_FP32_SIMT: 1e-5, tb.PREC_TF32: 3e-3}
-PRECS = [tb.PREC_TF32_BF16X2, tb.PREC_TF32X3, tb.PREC_TF32, tb.PREC_FP32_SIMT]
+TOL = {tb.PREC_F16X3: 1e-5, tb.PREC_TF32_BF16X2: 1e-5, tb.PREC_TF32X3: 1e-5, tb.PREC_FP32_SIMT: 1e-5, tb.PREC_TF32: 3e-3}
+PRECS = [tb.PREC_F16X3, tb.PREC_TF32_BF16X2, tb.PREC_TF32X3, tb.PREC_TF32, tb.PREC_FP32_SIMT]
+DEFAULT_PREC = tb.PREC_F16X3
 
 
 @pytest.fixture(scope="module")
 def ctx():
     c = tb.Context(0)
     yield c
-    c.set_precision(tb.PREC_TF32_BF16X2)
+    c.set_precision(DEFAULT_PREC)
 
 
 def rel(got, ref):
@@ -52,7 +53,7 @@ def test_fflayer_golden(ctx, prec):
     for name, t in zip(("A", "dX", "dW", "db"), got):
         close(t, g[name], TOL[prec], name)
     close(nn.fflayer_fwd(ctx.from_numpy(g["X"]), ctx.from_numpy(g["W"]), ctx.from_numpy(g["b"])), g["A"], TOL[prec], "fwd")
-    ctx.set_precision(tb.PREC_TF32_BF16X2)
+    ctx.set_precision(DEFAULT_PREC)
 
 
 # empty, single-sample, ragged (not multiples of any tile), one-wide, and multi-tile shapes
@@ -79,7 +80,7 @@ def test_fflayer_fwd_grad_shapes(ctx, prec, B, i, o):
     for name, a, c, r in zip(("dX", "dW", "db"), g1, g2, ref[1:]):
         close(a, r, TOL[prec], name + " (recompute)")
         close(c, r, TOL[prec], name + " (saved A)")
-    ctx.set_precision(tb.PREC_TF32_BF16X2)
+    ctx.set_precision(DEFAULT_PREC)
 
 
 def test_fflayer_empty_batch(ctx):
@@ -157,7 +158,7 @@ def test_mlp_softmax_ce_golden(ctx, prec):
     for l in range(3):
         close(dWs[l], g[f"dW{l}"], t, f"dW{l}"); close(dbs[l], g[f"db{l}"], t, f"db{l}")
     close(nn.mlp_fwd(Ws, bs, [tb.ACT_LOGISTIC, tb.ACT_LOGISTIC, tb.ACT_SOFTMAX], ctx.from_numpy(g["X"])), g["A"], t, "mlp_fwd")
-    ctx.set_precision(tb.PREC_TF32_BF16X2)
+    ctx.set_precision(DEFAULT_PREC)
 
 
 @pytest.mark.parametrize("acts,loss", [(["logistic", "logistic", "softmax"], "crossEntropy"), (["logistic", "logistic"], "squaredError"),
@@ -261,7 +262,7 @@ def test_gemm_all_transposition_views(ctx, prec, n, k, m):
     t = TOL[prec]
     close(da.gemm(db_), a @ b, t, "NN"); close(dat.gemm(db_), a @ b, t, "TN"); close(da.gemm(dbt), a @ b, t, "NT"); close(dat.gemm(dbt), a @ b, t, "TT")
     close(da.gemm(db_, 0.5, -2.0, dc), 0.5 * a @ b - 2.0 * c, t, "alpha/beta")
-    ctx.set_precision(tb.PREC_TF32_BF16X2)
+    ctx.set_precision(DEFAULT_PREC)
 
 
 GMUL_CASES = [((), (5,), ()), ((4,), (), (3,)), ((4,), (6,), ()), ((), (6,), (5,)), ((4,), (6,), (5,)), ((3, 4), (5,), (6,)),
@@ -403,7 +404,7 @@ def test_config3_mnist_shaped_mlp_full_batch(ctx):
 @pytest.mark.parametrize("B,n_chunks", [(1000, 3), (64, 0), (5000, 8)])
 def test_host_buffer_entry_point_pipelined(ctx, B, n_chunks):
     """tops_fflayer_fwd_grad_host: host X/dA in, chunked H2D overlapped with compute, dW/db accumulated across chunks."""
-    ctx.set_precision(tb.PREC_TF32_BF16X2)
+    ctx.set_precision(DEFAULT_PREC)
     rng = np.random.default_rng(77 + B)
     i, o = 96, 72
     X = rng.uniform(-1, 1, (B, i)).astype(np.float32); dA = rng.normal(size=(B, o)).astype(np.float32)
@@ -417,7 +418,7 @@ def test_host_buffer_entry_point_pipelined(ctx, B, n_chunks):
     assert np.array_equal(packed.numpy(), g)
 
 
-@pytest.mark.parametrize("prec", [tb.PREC_TF32_BF16X2, tb.PREC_TF32X3, tb.PREC_TF32])
+@pytest.mark.parametrize("prec", [tb.PREC_F16X3, tb.PREC_TF32_BF16X2, tb.PREC_TF32X3, tb.PREC_TF32])
 @pytest.mark.parametrize("B", [129, 255, 257, 385, 512])
 def test_cta_pair_tile_edges(ctx, prec, B):
     """Row counts around the 128/256-row boundaries of the CTA-pair (cta_group::2) tiles: the peer CTA of the last pair owns

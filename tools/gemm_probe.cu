@@ -1,5 +1,6 @@
 // Standalone bring-up / tuning probe for the tcgen05 GEMM engine (not part of the product library).
-//   gemm_probe dtype passes major_a major_b M N K block_n epi split_k iters [max_ctas]
+//   gemm_probe dtype passes major_a major_b M N K block_n epi split_k iters [max_ctas chunk_kb no_tma cta_group]
+//   dtype: 0 fp32 (passes 1/2/3), 1 bf16, 2 fp16 pairs (F16X3: the probe splits the fp32 operands itself)
 // Checks the result against a double-precision reference computed on the GPU (on a row subset for big M)
 // and, for fp32 single-pass, reports whether the tensor core truncates or rounds fp32 -> tf32.
 #include <cuda_bf16.h>
@@ -11,6 +12,7 @@
 #include <vector>
 
 #include "../tensor_ops_b200/csrc/gemm_sm100.h"
+#include "../tensor_ops_b200/csrc/kernels.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
@@ -46,6 +48,7 @@ __global__ void fill_rand(float* p, long long n, unsigned seed, float scale) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
     p[i] = scale * (((z >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0);
 }
+__global__ void mul_inv_scales(const float* sa2, const float* sb2, float* out) { out[0] = sa2[1] * sb2[1]; }
 __global__ void to_bf16(const float* s, __nv_bfloat16* d, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) d[i] = __float2bfloat16_rn(s[i]);
@@ -82,11 +85,38 @@ int main(int argc, char** argv) {
         to_bf16<<<(b_rows * b_cols + 255) / 256, 256>>>(Bf, Bb, b_rows * b_cols);
         A = Ab; B = Bb;
     }
+    void *A2 = nullptr, *B2 = nullptr; float* acc_scale = nullptr;
+    if (dtype == 2) {   // F16X3: per-tensor fp16 pairs of both operands
+        unsigned* mx; float* sc; int64_t launches = 0;
+        CK(cudaMalloc(&mx, 8)); CK(cudaMemset(mx, 0, 8)); CK(cudaMalloc(&sc, 5 * 4));
+        void *A1, *B1;
+        CK(cudaMalloc(&A1, a_rows * a_cols * 2)); CK(cudaMalloc(&A2, a_rows * a_cols * 2));
+        CK(cudaMalloc(&B1, b_rows * b_cols * 2)); CK(cudaMalloc(&B2, b_rows * b_cols * 2));
+        tops::k::LaunchCtx lc{0, prop.multiProcessorCount, &launches};
+        cudaEvent_t s0, s1; CK(cudaEventCreate(&s0)); CK(cudaEventCreate(&s1));
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaMemset(mx, 0, 8));
+            CK(cudaEventRecord(s0));
+            tops::k::absmax_bits(lc, Af, a_rows * a_cols, mx);
+            tops::k::split_f16_tensor(lc, Af, a_rows * a_cols, mx, A1, A2, sc);
+            CK(cudaEventRecord(s1));
+            tops::k::absmax_bits(lc, Bf, b_rows * b_cols, mx + 1);
+            tops::k::split_f16_tensor(lc, Bf, b_rows * b_cols, mx + 1, B1, B2, sc + 2);
+        }
+        mul_inv_scales<<<1, 1>>>(sc, sc + 2, sc + 4);
+        CK(cudaDeviceSynchronize());
+        float sms; CK(cudaEventElapsedTime(&sms, s0, s1));
+        float hs[5]; CK(cudaMemcpy(hs, sc, 20, cudaMemcpyDeviceToHost));
+        printf("  f16 pair split of A (%lld elements): absmax + split %.4f ms = %.0f GB/s; scales A %g B %g\n", a_rows * a_cols, sms,
+               8.0 * a_rows * a_cols / (sms * 1e-3) / 1e9 + 4.0 * a_rows * a_cols / (sms * 1e-3) / 1e9, hs[0], hs[2]);
+        A = A1; B = B1; acc_scale = sc + 4;
+    }
     CK(cudaDeviceSynchronize());
 
     tops::GemmCall c{};
     c.dtype = dtype; c.passes = passes; c.M = M; c.N = N; c.K = K;
     c.A = A; c.lda = lda; c.major_a = ma; c.B = B; c.ldb = ldb; c.major_b = mb;
+    c.A2 = A2; c.B2 = B2; c.acc_scale_ptr = acc_scale;
     c.epi = epi; c.act = 0; c.alpha = 1.f; c.beta = 0.f; c.out0 = C; c.ld_out0 = N;
     c.bias = (epi == 2) ? bias : nullptr;
     c.split_k = split; c.block_n = bn; c.max_ctas = max_ctas; c.chunk_kb = chunk_kb; c.no_tma_epilogue = no_tma; c.cta_group = cg;
