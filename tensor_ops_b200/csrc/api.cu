@@ -32,6 +32,7 @@ struct tops_ctx {
     // init, so it drains every 2 k-blocks (6e-7); the gradient GEMMs every 4 (1.1e-6, 7 % faster).  TOPS_F16X3_CHUNK / _FWD_CHUNK override.
     int f16x3_chunk_kb = 4;
     int f16x3_fwd_chunk_kb = 2;
+    int f16x3_fwd_head_kb = 4;    // first two chunks of every tile of the fused forward GEMM (lookahead for its epilogue); TOPS_F16X3_FWD_HEAD
     struct SplitEntry { const void* src; int64_t rows, cols; void* hi; void* lo; long long ld; float* scale2; };
     struct SplitScope* split_scope = nullptr;   // fp16 pairs already made inside the current API call
     int64_t launches = 0;
@@ -244,7 +245,10 @@ int run_gemm_f16x3(tops_ctx* ctx, const GemmCall& c0) {
     c.B = b.hi; c.B2 = b.lo; c.ldb = b.ld;
     c.B16 = c.Blo16 = nullptr;
     c.acc_scale_ptr = (const float*)sc->data;
-    if (c.chunk_kb <= 0) c.chunk_kb = c0.aux0 != nullptr ? ctx->f16x3_fwd_chunk_kb : ctx->f16x3_chunk_kb;
+    if (c.chunk_kb <= 0) {
+        c.chunk_kb = c0.aux0 != nullptr ? ctx->f16x3_fwd_chunk_kb : ctx->f16x3_chunk_kb;
+        if (c0.aux0 != nullptr) c.chunk_head_kb = ctx->f16x3_fwd_head_kb;
+    }
     return run_gemm(ctx, c);
 }
 
@@ -332,6 +336,7 @@ extern "C" int tops_init(int device, tops_ctx** out) {
     memset(ctx->wd_host, 0, 64);
     if (const char* e = getenv("TOPS_F16X3_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->f16x3_chunk_kb = v; }
     if (const char* e = getenv("TOPS_F16X3_FWD_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->f16x3_fwd_chunk_kb = v; }
+    if (const char* e = getenv("TOPS_F16X3_FWD_HEAD")) { const int v = atoi(e); if (v >= 0 && v <= 64) ctx->f16x3_fwd_head_kb = v; }
     *out = ctx;
     return TOPS_OK;
 }
@@ -999,7 +1004,7 @@ int layer_fwd_grad_f16x3(tops_ctx* ctx, const LayerShapes& s, const void* X, con
         g.out0 = A; g.ld_out0 = s.o; g.aux0 = dA; g.ld_aux0 = s.o;
         g.out1 = z1->data; g.out1b = z2->data; g.ld_out1 = s.o; g.out1_pair = 1; g.out1_scale_ptr = scal + 1; g.out1_row_scale = rsX;
         g.acc_scale_ptr = scal + 0; g.row_scale = rsX; g.row_scale_inv = 0;
-        g.chunk_kb = ctx->f16x3_fwd_chunk_kb;
+        g.chunk_kb = ctx->f16x3_fwd_chunk_kb; g.chunk_head_kb = ctx->f16x3_fwd_head_kb;
         if (db) {
             if (!accumulate) CUDA_TRY(ctx, cudaMemsetAsync(db, 0, sizeof(float) * (size_t)s.o, ctx->stream));
             g.colsum = db; g.colsum_src = 2; g.colsum_fused = &db_fused;

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -121,7 +122,8 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
         if (tma_epi && has_out1 && c.out1_pair)   // fp16 planes: 16-byte aligned rows of 2-byte elements
             tma_epi = c.out1b && (reinterpret_cast<uintptr_t>(c.out1) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.out1b) & 15) == 0 && ((size_t)c.ld_out1 * 2) % 16 == 0;
         else if (tma_epi && has_out1) tma_epi = aligned(c.out1, c.ld_out1);
-        if (tma_epi && has_aux) tma_epi = make_map(&tm[2], c.io_bf16 ? 1 : 0, c.aux0, c.N, c.M, c.ld_aux0, 32, 32, c.io_bf16 ? SWZ_64 : SWZ_128);
+        // aux boxes: 32 rows x 32 columns (fp32: 128-byte rows, bf16: 64-byte rows); F16X3 works on 32 x 16 fp32 sub-blocks (64-byte rows)
+        if (tma_epi && has_aux) tma_epi = make_map(&tm[2], c.io_bf16 ? 1 : 0, c.aux0, c.N, c.M, c.ld_aux0, c.dtype == 2 ? 16 : 32, 32, (c.io_bf16 || c.dtype == 2) ? SWZ_64 : SWZ_128);
     }
     if (c.out1_pair && !tma_epi) return fail(-1, "gemm: the fp16-pair output needs the staged epilogue (16-byte aligned rows)");
     if ((c.acc_scale_ptr || c.row_scale || c.out1_pair) && passes < 2) return fail(-1, "gemm: accumulator scaling / pair output exist in the chunked kernels only");
@@ -158,6 +160,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     // chunk_kb k-blocks (12 MMAs each) is promoted to round-to-nearest fp32 register sums; 4 k-blocks = 128 K-elements.
     // F16X3: k-blocks hold 64 K-elements and 12 MMAs; 2 k-blocks = 128 K-elements = 24 MMAs per chunk.
     p.chunk_kb = c.chunk_kb > 0 ? c.chunk_kb : (c.dtype == 2 ? 2 : 4);
+    p.chunk_head_kb = c.chunk_head_kb > p.chunk_kb ? c.chunk_head_kb : p.chunk_kb;
     p.acc_scale_ptr = c.acc_scale_ptr; p.row_scale = c.row_scale; p.row_scale_inv = c.row_scale_inv;
     p.out1_pair = c.out1_pair; p.out1b = c.out1b; p.out1_scale_ptr = c.out1_scale_ptr; p.out1_row_scale = c.out1_row_scale;
     p.epi = c.epi; p.act = c.act; p.alpha = c.alpha; p.beta = c.beta;
@@ -167,6 +170,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     p.bias = c.bias; p.loss = c.loss;
     p.io_bf16 = c.io_bf16;
     p.watchdog = watchdog_dev;
+    { static const int dbg = getenv("TOPS_GEMM_DEBUG") ? atoi(getenv("TOPS_GEMM_DEBUG")) : 0; p.debug = dbg; }
     p.tma_epi = tma_epi ? 1 : 0;
     // fused column sums ride on the staged blocks of the TMA epilogue; tell the caller whether they were produced
     p.colsum = (tma_epi && c.colsum_src != 0) ? c.colsum : nullptr;

@@ -57,6 +57,9 @@ struct GemmParams {
     int split_k;        // number of K partitions (>= 1)
     int kb_per_split;   // k-blocks per partition
     int chunk_kb;       // 3-pass only: k-blocks accumulated in TMEM before promotion to fp32 registers (>= 1)
+    int chunk_head_kb;  // chunked kernels: length of the FIRST TWO chunks of a work item (>= chunk_kb).  The two TMEM buffers let the MMA
+                        // warp run two chunks into the next work item while the epilogue warps finish the previous one; longer head
+                        // chunks buy the fused epilogue that much more time, at the accuracy of a longer TMEM accumulation on them
     int epi, act;
     float alpha, beta;
     void* out0; long long ld_out0;
@@ -87,6 +90,7 @@ struct GemmParams {
     const float* out1_scale_ptr;  // device scalar, NULL = 1
     const float* out1_row_scale;  // [M], NULL = 1
     unsigned int* watchdog;   // mapped host memory, 2 words
+    int debug;                // TOPS_GEMM_DEBUG bit mask (A/B experiments): 1 = no specialised forward epilogue
 };
 
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
@@ -114,7 +118,9 @@ struct GemmCfg {
     // epilogue staging: 32x32-element blocks (4 KiB fp32 / 2 KiB bf16) per epilogue warp, moved by TMA.
     // 1-pass: one block for the aux operand (prefetched one chunk ahead) + one for outputs; 3-pass: one shared block.
     static constexpr int EPI_WARPS = EPI_THREADS / 32;
-    static constexpr int EPI_W = 32;                                       // columns per epilogue block
+    // columns per epilogue block.  F16X3: 16, so that an aux block AND an output block (2 KiB each) fit beside three 64 KiB stages
+    // and the aux operand of sub-block c+1 arrives by TMA while sub-block c is being computed and written
+    static constexpr int EPI_W = PRESPLIT ? 16 : 32;
     static constexpr int EPI_BLOCK_BYTES = 32 * EPI_W * IO_BYTES;          // 4096 (fp32, 128-byte rows) / 2048 (bf16, 64-byte rows)
     // two blocks per warp (aux operand prefetched while the previous block is written out) when the pipeline stages leave
     // room for them, otherwise one block shared by the aux operand and the outputs
@@ -300,14 +306,16 @@ __device__ __forceinline__ void epi_direct(const GemmParams& p, int row, int col
 // so that both the thread side (lane = row, 16-byte accesses) and the TMA side are bank-conflict free:
 //   128-byte rows, SWIZZLE_128B: 16B chunk j of row r lives at r*128 + ((j ^ (r & 7)) << 4)
 //    64-byte rows, SWIZZLE_64B : 16B chunk j of row r lives at r*64  + ((j ^ ((r >> 1) & 3)) << 4)
+//    32-byte rows (thread-written only): chunk j of row r lives at r*32 + ((j ^ ((r >> 2) & 1)) << 4)
 template <int ROWB> __device__ __forceinline__ int stage_off(int r, int j) {
     if constexpr (ROWB == 128) return r * 128 + ((j ^ (r & 7)) << 4);
-    else return r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
+    else if constexpr (ROWB == 64) return r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
+    else return r * 32 + ((j ^ ((r >> 2) & 1)) << 4);
 }
 template <typename IO, int W>
 __device__ __forceinline__ void stage_read_row(uint32_t buf, int r, float (&x)[W]) {
     constexpr int ROWB = W * (int)sizeof(IO);
-    static_assert(ROWB == 64 || ROWB == 128, "staging rows are 64 or 128 bytes");
+    static_assert(ROWB == 64 || ROWB == 128, "TMA-filled staging rows are 64 or 128 bytes");
 #pragma unroll
     for (int j = 0; j < ROWB / 16; ++j) {
         const uint4 u = ptx::lds128(buf + stage_off<ROWB>(r, j));
@@ -343,9 +351,9 @@ __device__ __forceinline__ void stage_write_row(uint32_t buf, int r, const float
 // The two planes are staged as 32 x W fp16 blocks (64-byte rows, SWIZZLE_64B layout) at `buf` and `buf + 32 * W * 2`.
 template <int W>
 __device__ __forceinline__ void stage_write_row_f16pair(uint32_t buf, int r, const float (&x)[W], float s) {
-    static_assert(W == 32, "64-byte fp16 rows");
+    static_assert(W == 32 || W == 16, "64- or 32-byte fp16 rows");
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < W / 8; ++j) {
         uint4 uh, ul;
         __half2* hh = reinterpret_cast<__half2*>(&uh);
         __half2* hl = reinterpret_cast<__half2*>(&ul);
@@ -356,8 +364,8 @@ __device__ __forceinline__ void stage_write_row_f16pair(uint32_t buf, int r, con
             const float2 hf = __half22float2(hh[e]);
             hl[e] = __floats2half2_rn(t0 - hf.x, t1 - hf.y);
         }
-        ptx::sts128(buf + stage_off<64>(r, j), uh);
-        ptx::sts128(buf + 32 * W * 2 + stage_off<64>(r, j), ul);
+        ptx::sts128(buf + stage_off<W * 2>(r, j), uh);
+        ptx::sts128(buf + 32 * W * 2 + stage_off<W * 2>(r, j), ul);
     }
 }
 // Column sums of a staged 32 x W block, added into colsum[col .. col+W) with one red per column (db = sum_s dZ[s,:]).
@@ -365,7 +373,19 @@ template <typename IO, int W>
 __device__ __forceinline__ void stage_colsum(uint32_t buf, int lane, int col, int N, float* colsum) {
     constexpr int ROWB = W * (int)sizeof(IO);
     constexpr int EPC = 16 / (int)sizeof(IO);          // elements per 16-byte chunk
-    static_assert(W == 32, "one column per lane");
+    if constexpr (W == 16) {                           // fp32, 64-byte rows: lane = (column, row parity); the two parities meet by shuffle
+        static_assert(sizeof(IO) == 4, "16-column blocks are fp32");
+        const int c = lane & 15, h = lane >> 4;
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 16; ++k)                   // row 2k + h: ((2k + h) >> 1) & 3 == k & 3, a compile-time constant per k
+            part[k & 3] += ptx::lds32f(buf + (2 * k + h) * 64 + (((c >> 2) ^ (k & 3)) << 4) + (c & 3) * 4);
+        float s = (part[0] + part[1]) + (part[2] + part[3]);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (h == 0 && col + c < N) atomicAdd(colsum + col + c, s);
+        return;
+    }
+    static_assert(W == 32 || W == 16, "one column per lane");
     float part[4] = {0.f, 0.f, 0.f, 0.f};            // independent partial sums: no 32-long dependent FADD chain
     constexpr int PERIOD = 8;                          // stage_off(r + 8, j) == stage_off(r, j) + 8 * ROWB for both layouts
 #pragma unroll
@@ -464,8 +484,12 @@ struct EpiWarp {
     float out1_s;          // out1_pair: this lane's (row's) scale for the fp16 pair of out1
 };
 
+// The staging block was last READ by this warp with ld.shared (generic proxy) and is about to be WRITTEN by the TMA engine (async
+// proxy): without a proxy fence the bulk copy can overtake those reads — measured: ~1e-3 of the dZ elements picked up the next
+// sub-block's dA once the epilogue became fast enough (callers __syncwarp() after their reads, then every lane fences).
 template <typename IO, int W>
 __device__ __forceinline__ void epi_issue_aux(const CUtensorMap* tmAux, EpiWarp& w, int lane, int row0, int col) {
+    ptx::fence_proxy_async_smem();
     if (lane == 0) {
         ptx::mbar_arrive_expect_tx(w.aux_bar, 32u * W * (uint32_t)sizeof(IO));
         ptx::tma_load_2d_s(w.aux_buf, tmAux, w.aux_bar, col, row0);
@@ -497,7 +521,7 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, const CUtensorMap
     if (p.colsum != nullptr && p.colsum_src == 1) stage_colsum<IO, W>(w.out_buf, lane, col, p.N, p.colsum);
     __syncwarp();
     if (has_out1) {
-        if constexpr (std::is_same<IO, float>::value && W == 32) {
+        if constexpr (std::is_same<IO, float>::value) {
             if (p.out1_pair) {   // out1 leaves as an fp16 pair (operand of the next F16X3 GEMMs); its column sums come from the fp32 values
                 if (p.colsum != nullptr && p.colsum_src == 2) {
                     stage_write_row<IO, W>(w.out_buf, lane, x);
@@ -519,6 +543,62 @@ __device__ __forceinline__ void epi_block(const GemmParams& p, const CUtensorMap
         if (p.colsum != nullptr && p.colsum_src == 2) stage_colsum<IO, W>(w.out_buf, lane, col, p.N, p.colsum);
         __syncwarp();
     }
+}
+
+// Interior blocks only (all 32 rows and W columns valid): staged 32 x W block -> global, no guards.  Valid for 64- and 32-byte
+// staging rows, whose swizzle term is the same for all rows one warp instruction apart (see stage_off).
+template <typename IO, int W>
+__device__ __forceinline__ void stage_store_interior(uint32_t buf, int lane, void* base, long long ld, int row0, int col) {
+    constexpr int ROWB = W * (int)sizeof(IO), CPR = ROWB / 16, EPC = 16 / (int)sizeof(IO), RPI = 32 / CPR;
+    static_assert(ROWB == 64 || ROWB == 32, "constant-swizzle layouts");
+    const int j = lane % CPR, rl = lane / CPR;
+    IO* g0 = reinterpret_cast<IO*>(base) + (long long)(row0 + rl) * ld + col + j * EPC;
+    const uint32_t s0 = buf + stage_off<ROWB>(rl, j);
+    uint4 u[CPR];
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) u[k] = ptx::lds128(s0 + k * (RPI * ROWB));
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) *reinterpret_cast<uint4*>(g0 + (long long)k * RPI * ld) = u[k];
+}
+
+// The hot epilogue of the F16X3 forward GEMM, written out without any of the generality of epi_block: one interior 32 x 16
+// sub-block of  A = logistic(acc + b),  dZ = dA * A (1 - A),  db += column sums of dZ,  (dZ1, dZ2) = fp16 pair of dZ * s.
+// (The generic path costs ~680 instructions per sub-block — every epilogue variant, dtype and edge case is compiled into one
+// stream that no longer fits the instruction cache; this one is ~300.)  v: in = scaled accumulators, lane = row.
+__device__ __forceinline__ void epi_fwd_pair_lean(const GemmParams& p, const CUtensorMap* tmAux, EpiWarp& w, int lane, int row0, int col, int next_col,
+                                                  float (&v)[16], volatile unsigned int* wd) {
+    float4 b4[4];                                      // bias first: independent of everything else, its latency hides behind the aux wait
+#pragma unroll
+    for (int g = 0; g < 4; ++g) b4[g] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + g);
+    if (!w.in_flight) epi_issue_aux<float, 16>(tmAux, w, lane, row0, col);
+    ptx::mbar_wait(w.aux_bar, w.consumed & 1, wd, 0x600);
+    ++w.consumed;
+    float x[16];
+    stage_read_row<float, 16>(w.aux_buf, lane, x);
+    __syncwarp();
+    w.in_flight = false;
+    if (next_col >= 0) epi_issue_aux<float, 16>(tmAux, w, lane, row0, next_col);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { v[g * 4] += b4[g].x; v[g * 4 + 1] += b4[g].y; v[g * 4 + 2] += b4[g].z; v[g * 4 + 3] += b4[g].w; }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const float a = act_apply(ACT_LOGISTIC, v[e]);
+        v[e] = a;
+        x[e] = x[e] * (a * (1.0f - a));
+    }
+    stage_write_row<float, 16>(w.out_buf, lane, v);
+    __syncwarp();
+    stage_store_interior<float, 16>(w.out_buf, lane, p.out0, p.ld_out0, row0, col);
+    __syncwarp();
+    stage_write_row<float, 16>(w.out_buf, lane, x);
+    __syncwarp();
+    stage_colsum<float, 16>(w.out_buf, lane, col, p.N, p.colsum);
+    __syncwarp();
+    stage_write_row_f16pair<16>(w.out_buf, lane, x, w.out1_s);
+    __syncwarp();
+    stage_store_interior<__half, 16>(w.out_buf, lane, p.out1, p.ld_out1, row0, col);
+    stage_store_interior<__half, 16>(w.out_buf + 32 * 16 * 2, lane, p.out1b, p.ld_out1, row0, col);
+    __syncwarp();
 }
 
 // 8 fp32 values -> 8 x bf16(x) and 8 x bf16(x - trunc_tf32(x))   (operands of the two bf16 correction passes)
@@ -618,6 +698,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int total_work = num_tiles * p.split_k;
     const int chunk_kb = kChunked ? p.chunk_kb : (1 << 30);
+    const int chunk_head_kb = kChunked ? max(p.chunk_head_kb, p.chunk_kb) : (1 << 28);
+    // chunk boundaries of a work item [kb0, kb1): two head chunks, then chunk_kb each — the MMA warp and the epilogue warps agree on it
+    auto chunk_len = [&](int kc, int kb0) { return (kc - kb0 < 2 * chunk_head_kb) ? chunk_head_kb : chunk_kb; };
 
     if (warp < 4) {
         if constexpr (kChunked) ptx::setmaxnreg_dec<48>();
@@ -696,8 +779,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int split = w / num_tiles;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
-                for (int kc = kb0; kc < kb1; kc += chunk_kb, ++it) {
-                    const int kce = min(kc + chunk_kb, kb1);
+                for (int kc = kb0, kce; kc < kb1; kc = kce, ++it) {
+                    kce = min(kc + chunk_len(kc, kb0), kb1);
                     const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
                     if constexpr (CG == 2) ptx::mbar_wait_cluster(&tmem_empty[acc], acc_ph ^ 1, wd, 0x200 + acc);
                     else ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, wd, 0x200 + acc);
@@ -796,7 +879,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
-    } else if (!kChunked) {
+    } else if constexpr (!kChunked) {
         // ===================================================== epilogue, 1-pass: warps 4-11, one TMEM buffer per work item
         ptx::setmaxnreg_inc<224>();
         constexpr int W = Cfg::EPI_W;
@@ -872,27 +955,30 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m0 = (tile / p.num_n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (tile % p.num_n_tiles) * BN;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+            constexpr int W = Cfg::EPI_W;
             if (tma && epi_has_aux(p) && m0 + q * 32 < p.M && n0 + half * HC < p.N) {   // first aux block: requested before the K loop
-                epi_issue_aux<float, 32>(&tmAux, ew, lane, m0 + q * 32, n0 + half * HC);
-                if (lane > 0 && lane < HC / 32 && n0 + half * HC + lane * 32 < p.N)       // the other blocks: into L2 during the K loop
-                    ptx::tma_prefetch_l2_2d(&tmAux, n0 + half * HC + lane * 32, m0 + q * 32);
+                epi_issue_aux<float, W>(&tmAux, ew, lane, m0 + q * 32, n0 + half * HC);
+                if (lane > 0 && lane < HC / W && n0 + half * HC + lane * W < p.N)         // the other blocks: into L2 during the K loop
+                    ptx::tma_prefetch_l2_2d(&tmAux, n0 + half * HC + lane * W, m0 + q * 32);
             }
             float sum[HC];
 #pragma unroll
             for (int e = 0; e < HC; ++e) sum[e] = 0.f;
-            for (int kc = kb0; kc < kb1; kc += chunk_kb, ++it) {
+            for (int kc = kb0; kc < kb1; kc += chunk_len(kc, kb0), ++it) {
                 const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
                 if constexpr (CG == 2) ptx::mbar_wait_cluster(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
                 else ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
                 ptx::tcgen05_fence_after();
                 const uint32_t t_row = tmem_base + acc * BN + half * HC + (static_cast<uint32_t>(q * 32) << 16);
+                // drain, software-pipelined: the tcgen05.ld of group c+1 is in flight while group c is added
+                uint32_t raw[2][16];
+                ptx::tmem_ld_32x32b_x16(t_row, raw[0]);
 #pragma unroll
                 for (int c = 0; c < HC / 16; ++c) {
-                    uint32_t raw[16];
-                    ptx::tmem_ld_32x32b_x16(t_row + c * 16, raw);
                     ptx::tmem_ld_wait();
+                    if (c + 1 < HC / 16) ptx::tmem_ld_32x32b_x16(t_row + (c + 1) * 16, raw[(c + 1) & 1]);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) sum[c * 16 + e] += __uint_as_float(raw[e]);   // fp32 add, round to nearest
+                    for (int e = 0; e < 16; ++e) sum[c * 16 + e] += __uint_as_float(raw[c & 1][e]);   // fp32 add, round to nearest
                 }
                 ptx::tcgen05_fence_before();
                 __syncwarp();
@@ -913,16 +999,37 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ew.out1_s = p.out1_scale_ptr != nullptr ? __ldg(p.out1_scale_ptr) : 1.0f;
                 if (p.out1_row_scale != nullptr && row < p.M) ew.out1_s *= __ldg(p.out1_row_scale + row);
             }
-            if (row0 < p.M) {
+            bool lean = false;
+            if constexpr (kPresplit) {   // hot case of the forward GEMM on an interior tile: the specialised sub-block code
+                lean = tma && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && p.out1_pair && p.colsum != nullptr && p.colsum_src == 2 &&
+                       p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && row0 + 32 <= p.M && n0 + half * HC + HC <= p.N && !(p.debug & 1);
+            }
+            if constexpr (kPresplit) {
+                if (lean) {
+#pragma unroll 1
+                    for (int c = 0; c < HC / 32; ++c) {
+                        const int col = n0 + half * HC + c * 32;
+                        epi_fwd_pair_lean(p, &tmAux, ew, lane, row0, col, col + 16, *reinterpret_cast<float (*)[16]>(&sum[0]), wd);
+                        epi_fwd_pair_lean(p, &tmAux, ew, lane, row0, col + 16, c + 1 < HC / 32 ? col + 32 : -1, *reinterpret_cast<float (*)[16]>(&sum[16]), wd);
+#pragma unroll
+                        for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];
+                    }
+                }
+            }
+            if (row0 < p.M && !lean) {
                 // ONE copy of the block code (the fused epilogue is large; unrolled four times it thrashes the instruction
                 // cache): always process sum[0..31], then rotate the register accumulators down by one block.
 #pragma unroll 1
                 for (int c = 0; c < HC / 32; ++c) {
-                    const int col = n0 + half * HC + c * 32;
-                    float (&v)[32] = *reinterpret_cast<float (*)[32]>(&sum[0]);   // the block is processed in place ...
-                    if (col < p.N) {
-                        if (tma) epi_block<float, 32, Cfg::EPI_SHARED>(p, &tmAux, ew, lane, row0, col, (c + 1 < HC / 32 && col + 32 < p.N) ? col + 32 : -1, v, loss_acc, wd);
-                        else if (row < p.M) epi_direct<32>(p, row, col, vec, v, loss_acc);
+#pragma unroll
+                    for (int u = 0; u < 32 / W; ++u) {                            // W = 16: two sub-blocks per rotation
+                        const int col = n0 + half * HC + c * 32 + u * W;
+                        float (&v)[W] = *reinterpret_cast<float (*)[W]>(&sum[u * W]);   // the block is processed in place ...
+                        if (col < p.N) {
+                            const bool more = (u + 1 < 32 / W || c + 1 < HC / 32) && col + W < p.N;
+                            if (tma) epi_block<float, W, Cfg::EPI_SHARED>(p, &tmAux, ew, lane, row0, col, more ? col + W : -1, v, loss_acc, wd);
+                            else if (row < p.M) epi_direct<W>(p, row, col, vec, v, loss_acc);
+                        }
                     }
 #pragma unroll
                     for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];       // ... and the accumulators rotate afterwards

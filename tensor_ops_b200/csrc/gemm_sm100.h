@@ -40,7 +40,8 @@ struct GemmCall {
     float* out0_mc;        // EPI_ATOMIC only: NVLS multicast alias of a buffer shaped like out0; finished split-K regions are pushed there once
     int* tile_counters;    // with out0_mc: zeroed int[ceil(M/128) * ceil(N/bn) * 8 + 16] region-arrival counters
     int no_tma_epilogue;   // 1 = force the direct register<->global epilogue (bring-up / A-B comparison)
-    int chunk_kb;   // 3-pass only: k-blocks per TMEM chunk before promotion to fp32 registers (0 = default 4)
+    int chunk_kb;   // chunked kernels: k-blocks per TMEM chunk before promotion to fp32 registers (0 = default: 4, F16X3 2)
+    int chunk_head_kb;   // chunked kernels: k-blocks in each of the first two chunks of a work item (0 = chunk_kb)
     const char* tag;   // profiling label (tops_profile_*), may be NULL
 };
 

@@ -15,6 +15,8 @@ KEYS = [
     ("sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.sum.per_second", "UTCHMMA tf32 rate"),
     ("sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.sum", "UTCHMMA bf16 ops (flop)"),
     ("sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.sum.per_second", "UTCHMMA bf16 rate"),
+    ("sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum", "UTCHMMA fp16 ops (flop)"),
+    ("sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum.per_second", "UTCHMMA fp16 rate"),
     ("sm__inst_executed_pipe_tmem.sum", "TMEM instructions"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),

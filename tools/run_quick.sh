@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 300 -k "fflayer or cta_pair or host" > gpurun_out/pytest_ff.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_ff.log
-tail -15 gpurun_out/pytest_ff.log
-timeout 300 python tools/parity_report.py > gpurun_out/parity.log 2>&1; cat gpurun_out/parity.log
-timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-side > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; cat gpurun_out/bench_quick.json; tail -3 gpurun_out/bench_quick.err
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+for cfg in "2 4" "2 0" "2 6"; do set -- $cfg
+echo "== fwd chunk $1 head $2"
+TOPS_F16X3_FWD_CHUNK=$1 TOPS_F16X3_FWD_HEAD=$2 timeout 300 python tools/parity_report.py 2>&1 | grep f16x3
+TOPS_F16X3_FWD_CHUNK=$1 TOPS_F16X3_FWD_HEAD=$2 timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-side 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['per_kernel_ms'])"
+done
