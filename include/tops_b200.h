@@ -182,6 +182,17 @@ int tops_fflayer_fwd_grad_host(tops_ctx*, const float* X_host, const float* dA_h
  * call, barrier.  (The reference has no parallelism; this completes the sum over samples its training fold performs serially.) */
 int tops_fflayer_fwd_grad_mc(tops_ctx*, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act, const tops_buf* dA,
                              tops_buf** A, tops_buf** dX, tops_buf** grads_local, void* grads_mc);
+/* Data-parallel step with the schedule owned by the library (SURVEY 8-b `tops_fflayer_step_dp`): forward, then dW and db into the
+ * packed buffer `grads` = [dW (o*i) || db (o)]; the event `grads_ready` (tops_event_create) is recorded as soon as they are
+ * complete and only then is the dX GEMM launched, leaving `reserve_sms` SMs free — dX does not depend on dW, so the caller's
+ * all-reduce of `grads` (NCCL on a stream that waits for the event, tops_stream_wait_event) overlaps it.  Sums what the
+ * reference's training fold accumulates one sample at a time (FeedForward.hs:131-148, app/Dots.hs:74-80). */
+int tops_fflayer_step_dp(tops_ctx*, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act, const tops_buf* dA,
+                         tops_buf** A, tops_buf** dX, tops_buf** grads, void* grads_ready, int reserve_sms);
+/* CUDA events for schedules that span streams (the handle is a cudaEvent_t). `stream` NULL = the context's current stream. */
+int tops_event_create(tops_ctx*, void** ev);
+int tops_event_destroy(tops_ctx*, void* ev);
+int tops_stream_wait_event(tops_ctx*, void* stream, void* ev);
 /* netGrad (FeedForward.hs:178-199) of a genNet-style network (FeedForward.hs:216-235) over a batch:
  *   layers l = 0..n-1 with W[l], b[l], acts[l]; loss on (A_out, Y); per-sample losses summed into loss_sum (rank 0).
  *   Outputs: A_out[B,o], loss_sum[], dX[B,i] (may be NULL to skip), dW[l], db[l]. */

@@ -82,6 +82,10 @@ PROTOTYPES = {
     "tops_mlp_fwd": (C.c_int, [c_ctx, C.c_int, c_bufp, c_bufp, C.POINTER(C.c_int), c_buf, c_bufp]),
     "tops_fflayer_fwd_grad_host": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_int64, c_buf, c_buf, C.c_int, C.c_int, c_bufp, c_bufp, c_bufp, C.c_void_p]),
     "tops_fflayer_fwd_grad_mc": (C.c_int, [c_ctx, c_buf, c_buf, c_buf, C.c_int, c_buf, c_bufp, c_bufp, c_bufp, C.c_void_p]),
+    "tops_fflayer_step_dp": (C.c_int, [c_ctx, c_buf, c_buf, c_buf, C.c_int, c_buf, c_bufp, c_bufp, c_bufp, C.c_void_p, C.c_int]),
+    "tops_event_create": (C.c_int, [c_ctx, C.POINTER(C.c_void_p)]),
+    "tops_event_destroy": (C.c_int, [c_ctx, C.c_void_p]),
+    "tops_stream_wait_event": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p]),
     "tops_sgd_step": (C.c_int, [c_ctx, C.c_int, c_bufp, c_bufp, C.c_double, c_bufp]),
 }
 

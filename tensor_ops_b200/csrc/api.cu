@@ -895,7 +895,7 @@ int fwd_gemm(tops_ctx* ctx, const LayerShapes& s, const void* X, const void* W, 
 // dX = dZ W  (optionally ⊙ act'(A_prev))
 // `db_prev` (optional, EPI_MUL_DACT only): the output IS dZ of the previous layer, so its column sums are that layer's db.
 int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, void* dX, int epi, int act, const void* Aprev,
-            float* db_prev = nullptr, int* db_fused = nullptr, const WSplit* ws = nullptr) {
+            float* db_prev = nullptr, int* db_fused = nullptr, const WSplit* ws = nullptr, int max_ctas = 0) {
     GemmCall g{};
     g.dtype = s.dtype == TOPS_BF16; g.M = (int)s.B; g.N = (int)s.i; g.K = (int)s.o;
     g.A = dZ; g.lda = s.o; g.major_a = MAJOR_K;
@@ -903,7 +903,7 @@ int dx_gemm(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* W, 
     if (ws) { g.B16 = ws->w16; g.Blo16 = ws->wlo16; }
     g.epi = epi; g.act = act; g.alpha = 1.f; g.tag = "gemm_dX";
     g.out0 = dX; g.ld_out0 = s.i; g.aux0 = Aprev; g.ld_aux0 = s.i;
-    g.io_bf16 = g.dtype;
+    g.io_bf16 = g.dtype; g.max_ctas = max_ctas;
     if (db_prev && epi == EPI_MUL_DACT && s.B > 0) {
         CUDA_TRY(ctx, cudaMemsetAsync(db_prev, 0, sizeof(float) * (size_t)s.i, ctx->stream));
         g.colsum = db_prev; g.colsum_src = 1; g.colsum_fused = db_fused;
@@ -928,13 +928,12 @@ int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, 
     int rc_ = run_gemm(ctx, g);
     if (counters) cudaFreeAsync(counters, ctx->stream);
     TRY(rc_);
-    if (db && !db_done && accumulate) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "accumulating db needs the fused column sums (aligned fp32/bf16 rows)");
-    if (db && !db_done) {
+    if (db && !db_done) {   // the forward epilogue could not fuse the column sums (rows not 16-byte aligned, FP32_SIMT, SIMT fallback)
         ProfScope prof_(ctx, "col_sums_db", 0.0, (s.dtype == TOPS_BF16 ? 2.0 : 4.0) * (double)s.B * s.o);
         float* ws = nullptr;
         CUDA_TRY(ctx, cudaMallocAsync((void**)&ws, sizeof(float) * 64 * (size_t)s.o, ctx->stream));
-        if (s.dtype == TOPS_BF16) k::col_sums_bf16(lc_of(ctx), dZ, s.B, s.o, db, ws);
-        else k::col_sums(lc_of(ctx), (const float*)dZ, s.B, s.o, db, ws);
+        if (s.dtype == TOPS_BF16) k::col_sums_bf16(lc_of(ctx), dZ, s.B, s.o, db, ws, accumulate);
+        else k::col_sums(lc_of(ctx), (const float*)dZ, s.B, s.o, db, ws, accumulate);
         cudaFreeAsync(ws, ctx->stream);
         TRY(check_launch(ctx, "col_sums"));
     }
@@ -972,8 +971,10 @@ int prep_wpair_f16(tops_ctx* ctx, const LayerShapes& s, const void* W, Tmp& tmp,
 }
 
 // X, dA, A, dX: device pointers to [B,i] / [B,o] fp32 row-major; dW [o,i], db [o] (nullable) fp32.  accumulate: dW/db are added to.
+// ev_grads (nullable): recorded on the stream as soon as dW and db are complete, i.e. BEFORE the dX GEMM is launched — a
+// data-parallel caller starts the all-reduce of [dW‖db] on another stream while dX runs on at most dx_max_ctas SMs (0 = all).
 int layer_fwd_grad_f16x3(tops_ctx* ctx, const LayerShapes& s, const void* X, const WPairF16& wp, const float* b, int act, const void* dA,
-                         void* A, void* dX, float* dW, float* db, bool accumulate, float* dW_mc) {
+                         void* A, void* dX, float* dW, float* db, bool accumulate, float* dW_mc, cudaEvent_t ev_grads = nullptr, int dx_max_ctas = 0) {
     Tmp tmp;
     int64_t xd[1] = {s.B * s.i}, zd[1] = {s.B * s.o}, rd[1] = {s.B}, sd[1] = {8};
     tops_buf *x1 = nullptr, *x2 = nullptr, *z1 = nullptr, *z2 = nullptr, *rs = nullptr, *sc = nullptr;
@@ -1031,6 +1032,7 @@ int layer_fwd_grad_f16x3(tops_ctx* ctx, const LayerShapes& s, const void* X, con
         if (counters) cudaFreeAsync(counters, ctx->stream);
         TRY(rc_);
     }
+    if (ev_grads) CUDA_TRY(ctx, cudaEventRecord(ev_grads, ctx->stream));
     // ---- dX = dZ W
     if (dX) {
         GemmCall g{};
@@ -1039,6 +1041,7 @@ int layer_fwd_grad_f16x3(tops_ctx* ctx, const LayerShapes& s, const void* X, con
         g.B = wp.w1; g.B2 = wp.w2; g.ldb = s.i; g.major_b = MAJOR_MN;
         g.epi = EPI_STORE; g.alpha = 1.f; g.out0 = dX; g.ld_out0 = s.i; g.tag = "gemm_dX";
         g.acc_scale_ptr = scal + 3; g.row_scale = rsX; g.row_scale_inv = 1; g.chunk_kb = ctx->f16x3_chunk_kb;
+        g.max_ctas = dx_max_ctas;
         TRY(run_gemm(ctx, g));
     }
     return TOPS_OK;
@@ -1197,6 +1200,68 @@ extern "C" int tops_fflayer_fwd_grad_mc(tops_ctx* ctx, const tops_buf* X, const 
     k::mc_push(lc_of(ctx), db, db_mc, s.o);            // o floats: the bias gradient joins the same multicast buffer
     TRY(check_launch(ctx, "mc_push"));
     if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr, nullptr, nullptr, &ws));
+    return TOPS_OK;
+}
+
+// ---- events (for schedules that span streams: the data-parallel step below)
+extern "C" int tops_event_create(tops_ctx* ctx, void** ev) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!ev) return set_err(ctx, TOPS_ERR_INVALID, "tops_event_create: NULL slot");
+    cudaEvent_t e;
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *ev = e;
+    return TOPS_OK;
+}
+extern "C" int tops_event_destroy(tops_ctx* ctx, void* ev) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (ev) CUDA_TRY(ctx, cudaEventDestroy((cudaEvent_t)ev));
+    return TOPS_OK;
+}
+extern "C" int tops_stream_wait_event(tops_ctx* ctx, void* stream, void* ev) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!ev) return set_err(ctx, TOPS_ERR_INVALID, "tops_stream_wait_event: NULL event");
+    CUDA_TRY(ctx, cudaStreamWaitEvent(stream ? (cudaStream_t)stream : ctx->stream, (cudaEvent_t)ev, 0));
+    return TOPS_OK;
+}
+
+// Data-parallel step, library-owned schedule: forward, dW (+ db) into the packed buffer `grads` = [dW (o*i) || db (o)], then the
+// event `grads_ready` is recorded and ONLY THEN the dX GEMM is launched — dX does not depend on dW, so the caller's all-reduce of
+// `grads` (NCCL on a communication stream that waits for the event) runs concurrently with it.  `reserve_sms` SMs are left free by
+// the persistent dX GEMM so that the collective's CTAs are scheduled at once instead of behind it.
+extern "C" int tops_fflayer_step_dp(tops_ctx* ctx, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act, const tops_buf* dA,
+                                    tops_buf** A, tops_buf** dX, tops_buf** grads, void* grads_ready, int reserve_sms) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    LayerShapes s; TRY(layer_shapes(ctx, X, W, b, &s)); TRY(check_act(ctx, act));
+    if (!dA || dA->rank != 2 || dA->dims[0] != s.B || dA->dims[1] != s.o || dA->dtype != s.dtype || dA->tr) return set_err(ctx, TOPS_ERR_SHAPE, "fflayer: dA[B,o] expected");
+    if (!grads) return set_err(ctx, TOPS_ERR_INVALID, "fflayer_step_dp: NULL grads slot");
+    if (reserve_sms < 0 || reserve_sms >= ctx->num_sms) return set_err(ctx, TOPS_ERR_INVALID, "fflayer_step_dp: reserve_sms out of range");
+    int64_t dAo[2] = {s.B, s.o}, dXs[2] = {s.B, s.i}, g_[1] = {s.o * s.i + s.o};
+    TRY(prep_out(ctx, A, s.dtype, 2, dAo));
+    if (dX) TRY(prep_out(ctx, dX, s.dtype, 2, dXs));
+    TRY(prep_out(ctx, grads, TOPS_F32, 1, g_));
+    float* dW = (float*)(*grads)->data; float* db = dW + s.o * s.i;
+    const int dx_ctas = reserve_sms > 0 ? ((ctx->num_sms - reserve_sms) & ~1) : 0;
+    cudaEvent_t ev = (cudaEvent_t)grads_ready;
+    Tmp tmp;
+    if (s.B == 0) {
+        CUDA_TRY(ctx, cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)(s.o * s.i + s.o), ctx->stream));
+        if (ev) CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
+        return TOPS_OK;
+    }
+    if (f16x3_layer_ok(ctx, s)) {
+        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp));
+        return layer_fwd_grad_f16x3(ctx, s, X->data, wp, b ? (const float*)b->data : nullptr, act, dA->data, (*A)->data, dX ? (*dX)->data : nullptr,
+                                    dW, db, false, nullptr, ev, dx_ctas);
+    }
+    SplitScope split_scope_(ctx);
+    tops_buf* dZ = nullptr;
+    TRY(alloc_buf(ctx, s.dtype, 2, dAo, &dZ)); tmp.keep(dZ);
+    WSplit ws; TRY(make_wsplit(ctx, W, tmp, &ws));
+    int db_fused = 0;
+    TRY(fwd_gemm(ctx, s, X->data, W->data, b ? (const float*)b->data : nullptr, act, EPI_BIAS_ACT_DZ, (*A)->data, dA->data, dZ->data, nullptr, db, &db_fused, false, &ws));
+    TRY(dw_db(ctx, s, dZ->data, X->data, dW, db, db_fused != 0));
+    if (ev) CUDA_TRY(ctx, cudaEventRecord(ev, ctx->stream));
+    if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr, nullptr, nullptr, &ws, dx_ctas));
     return TOPS_OK;
 }
 

@@ -564,12 +564,9 @@ __device__ __forceinline__ void stage_store_interior(uint32_t buf, int lane, voi
 // The hot epilogue of the F16X3 forward GEMM, written out without any of the generality of epi_block: one interior 32 x 16
 // sub-block of  A = logistic(acc + b),  dZ = dA * A (1 - A),  db += column sums of dZ,  (dZ1, dZ2) = fp16 pair of dZ * s.
 // (The generic path costs ~680 instructions per sub-block — every epilogue variant, dtype and edge case is compiled into one
-// stream that no longer fits the instruction cache; this one is ~300.)  v: in = scaled accumulators, lane = row.
+// stream that no longer fits the instruction cache; this one is ~300.)  v: in = scaled accumulators + bias, lane = row.
 __device__ __forceinline__ void epi_fwd_pair_lean(const GemmParams& p, const CUtensorMap* tmAux, EpiWarp& w, int lane, int row0, int col, int next_col,
                                                   float (&v)[16], volatile unsigned int* wd) {
-    float4 b4[4];                                      // bias first: independent of everything else, its latency hides behind the aux wait
-#pragma unroll
-    for (int g = 0; g < 4; ++g) b4[g] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + g);
     if (!w.in_flight) epi_issue_aux<float, 16>(tmAux, w, lane, row0, col);
     ptx::mbar_wait(w.aux_bar, w.consumed & 1, wd, 0x600);
     ++w.consumed;
@@ -578,8 +575,6 @@ __device__ __forceinline__ void epi_fwd_pair_lean(const GemmParams& p, const CUt
     __syncwarp();
     w.in_flight = false;
     if (next_col >= 0) epi_issue_aux<float, 16>(tmAux, w, lane, row0, next_col);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) { v[g * 4] += b4[g].x; v[g * 4 + 1] += b4[g].y; v[g * 4 + 2] += b4[g].z; v[g * 4 + 3] += b4[g].w; }
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
         const float a = act_apply(ACT_LOGISTIC, v[e]);
@@ -986,23 +981,33 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
-            if (p.acc_scale_ptr != nullptr || p.row_scale != nullptr) {   // undo the power-of-two operand scaling (exact)
-                float rs = p.acc_scale_ptr != nullptr ? __ldg(p.acc_scale_ptr) : 1.0f;
-                if (p.row_scale != nullptr && row < p.M) {
-                    const float r = __ldg(p.row_scale + row);
-                    rs *= p.row_scale_inv ? __frcp_rn(r) : r;   // powers of two: exact
-                }
-#pragma unroll
-                for (int e = 0; e < HC; ++e) sum[e] *= rs;
-            }
-            if (p.out1_pair) {
-                ew.out1_s = p.out1_scale_ptr != nullptr ? __ldg(p.out1_scale_ptr) : 1.0f;
-                if (p.out1_row_scale != nullptr && row < p.M) ew.out1_s *= __ldg(p.out1_row_scale + row);
-            }
             bool lean = false;
             if constexpr (kPresplit) {   // hot case of the forward GEMM on an interior tile: the specialised sub-block code
                 lean = tma && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && p.out1_pair && p.colsum != nullptr && p.colsum_src == 2 &&
                        p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && row0 + 32 <= p.M && n0 + half * HC + HC <= p.N && !(p.debug & 1);
+            }
+            {
+                float rs = p.acc_scale_ptr != nullptr ? __ldg(p.acc_scale_ptr) : 1.0f;   // undo the power-of-two operand scaling (exact)
+                if (p.row_scale != nullptr && row < p.M) {
+                    const float r = __ldg(p.row_scale + row);
+                    rs *= p.row_scale_inv ? __frcp_rn(r) : r;   // powers of two: exact
+                }
+                if (lean) {   // bias folded into the same pass: 32 independent 16-byte broadcast loads instead of 4 per sub-block
+                    const float4* b4p = reinterpret_cast<const float4*>(p.bias + n0 + half * HC);
+#pragma unroll
+                    for (int g = 0; g < HC / 4; ++g) {
+                        const float4 b4 = __ldg(b4p + g);
+                        sum[g * 4] = fmaf(sum[g * 4], rs, b4.x); sum[g * 4 + 1] = fmaf(sum[g * 4 + 1], rs, b4.y);
+                        sum[g * 4 + 2] = fmaf(sum[g * 4 + 2], rs, b4.z); sum[g * 4 + 3] = fmaf(sum[g * 4 + 3], rs, b4.w);
+                    }
+                } else if (p.acc_scale_ptr != nullptr || p.row_scale != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < HC; ++e) sum[e] *= rs;
+                }
+            }
+            if (p.out1_pair) {
+                ew.out1_s = p.out1_scale_ptr != nullptr ? __ldg(p.out1_scale_ptr) : 1.0f;
+                if (p.out1_row_scale != nullptr && row < p.M) ew.out1_s *= __ldg(p.out1_row_scale + row);
             }
             if constexpr (kPresplit) {
                 if (lean) {

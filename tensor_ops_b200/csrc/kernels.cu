@@ -266,7 +266,7 @@ __global__ void k_colsum_partial(const TIn* __restrict__ x, const float* __restr
         if (c < cols) partial[(int64_t)blockIdx.y * cols + c] = s;
     }
 }
-__global__ void k_colsum_final(const float* __restrict__ partial, int chunks, int64_t cols, float alpha, float beta, const float* __restrict__ y, float* __restrict__ out) {
+__global__ void k_colsum_final(const float* __restrict__ partial, int chunks, int64_t cols, float alpha, float beta, const float* y, float* out) {
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cols; c += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int k2 = 0; k2 < chunks; ++k2) s += partial[(int64_t)k2 * cols + c];
@@ -579,21 +579,21 @@ static int colsum_chunks(const LaunchCtx& lc, int64_t rows, int64_t cols) {
     if (chunks < 1) chunks = 1;
     return (int)chunks;
 }
-void col_sums(const LaunchCtx& lc, const float* x, int64_t rows, int64_t cols, float* out, float* ws) {
+void col_sums(const LaunchCtx& lc, const float* x, int64_t rows, int64_t cols, float* out, float* ws, bool accumulate) {
     if (cols <= 0) return;
     const int chunks = colsum_chunks(lc, rows, cols);
     const int64_t rpc = (rows + chunks - 1) / chunks;
     dim3 g((unsigned)((cols + 127) / 128), (unsigned)chunks);
     k_colsum_partial<float><<<g, 256, 0, lc.stream>>>(x, nullptr, rows, cols, rpc, ws); count(lc);
-    k_colsum_final<<<grid_for(lc, cols), kThreads, 0, lc.stream>>>(ws, chunks, cols, 1.0f, 0.f, nullptr, out); count(lc);
+    k_colsum_final<<<grid_for(lc, cols), kThreads, 0, lc.stream>>>(ws, chunks, cols, 1.0f, 1.0f, accumulate ? out : nullptr, out); count(lc);
 }
-void col_sums_bf16(const LaunchCtx& lc, const void* x, int64_t rows, int64_t cols, float* out, float* ws) {
+void col_sums_bf16(const LaunchCtx& lc, const void* x, int64_t rows, int64_t cols, float* out, float* ws, bool accumulate) {
     if (cols <= 0) return;
     const int chunks = colsum_chunks(lc, rows, cols);
     const int64_t rpc = (rows + chunks - 1) / chunks;
     dim3 g((unsigned)((cols + 127) / 128), (unsigned)chunks);
     k_colsum_partial<__nv_bfloat16><<<g, 256, 0, lc.stream>>>((const __nv_bfloat16*)x, nullptr, rows, cols, rpc, ws); count(lc);
-    k_colsum_final<<<grid_for(lc, cols), kThreads, 0, lc.stream>>>(ws, chunks, cols, 1.0f, 0.f, nullptr, out); count(lc);
+    k_colsum_final<<<grid_for(lc, cols), kThreads, 0, lc.stream>>>(ws, chunks, cols, 1.0f, 1.0f, accumulate ? out : nullptr, out); count(lc);
 }
 
 void ger(const LaunchCtx& lc, const float* x, const float* y, float* out, int64_t n, int64_t m) {

@@ -60,8 +60,9 @@ void mc_push(const LaunchCtx&, const float* src, float* out_mc, int64_t n);
 void sum_all(const LaunchCtx&, const float* x, int64_t n, float* out_scalar, float* workspace /* >= 1024 floats */);
 void dot(const LaunchCtx&, const float* x, const float* y, int64_t n, float* out_scalar, float* workspace);
 void trace(const LaunchCtx&, const float* a, int64_t n, int64_t ld, float* out_scalar);
-void col_sums(const LaunchCtx&, const float* x, int64_t rows, int64_t cols, float* out, float* workspace /* >= 64*cols floats */);
-void col_sums_bf16(const LaunchCtx&, const void* x, int64_t rows, int64_t cols, float* out, float* workspace);
+// accumulate: out += column sums (out is read, elementwise, by the thread that writes it)
+void col_sums(const LaunchCtx&, const float* x, int64_t rows, int64_t cols, float* out, float* workspace /* >= 64*cols floats */, bool accumulate = false);
+void col_sums_bf16(const LaunchCtx&, const void* x, int64_t rows, int64_t cols, float* out, float* workspace, bool accumulate = false);
 
 // ---- BLAS-2 / layout
 void ger(const LaunchCtx&, const float* x, const float* y, float* out, int64_t n, int64_t m);

@@ -95,3 +95,49 @@ class FusedGradAllReduce:
     def end(self):
         """All ranks' multimem reductions have been issued and completed: the local replica now holds the summed gradient."""
         self.handle.barrier(channel=1)
+
+
+class OverlappedStep:
+    """The data-parallel ffLayer step with the gradient all-reduce overlapped with the dX GEMM (tops_fflayer_step_dp).
+
+    The library launches forward -> dW(+db) -> [event] -> dX on the compute stream; this helper owns a communication stream that
+    waits for the event and runs the NCCL all-reduce of the packed [dW‖db] while dX is still computing (dX does not depend on
+    dW).  `step()` returns after queueing everything; the compute stream is made to wait for the collective, so work queued
+    after `step()` sees the summed gradient.  `reserve_sms` SMs are left to the collective by the persistent dX GEMM.
+    Without a process group (single GPU) it degenerates to the plain call."""
+
+    def __init__(self, ctx, layout: PackedLayout, device, reserve_sms: int = 8, group=None):
+        import ctypes as C
+        import torch
+        from . import _lib as L
+        self.ctx, self.layout, self.group, self.reserve_sms = ctx, layout, group, int(reserve_sms)
+        self.packed_t = torch.zeros(layout.numel, dtype=torch.float32, device=device)
+        self.packed = ctx.wrap_torch(self.packed_t)
+        self.comm_stream = torch.cuda.Stream(device=device)
+        ev = C.c_void_p()
+        ctx.check(L.lib.tops_event_create(ctx.h, C.byref(ev)))
+        self._ev = ev
+        self._L, self._C, self._torch = L, C, torch
+
+    def close(self):
+        if self._ev is not None:
+            self.ctx.check(self._L.lib.tops_event_destroy(self.ctx.h, self._ev))
+            self._ev = None
+
+    def step(self, X, W, b, dA, A=None, dX=None, act=None):
+        """Queues one step; returns (A, dX, packed gradient CuTensor)."""
+        import torch.distributed as dist
+        L, C, torch = self._L, self._C, self._torch
+        act = L.ACT_LOGISTIC if act is None else act
+        from .tensor import CuTensor
+        slots = [L.c_buf(A.b.value) if A is not None else L.c_buf(), L.c_buf(dX.b.value) if dX is not None else L.c_buf(), L.c_buf(self.packed.b.value)]
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        self.ctx.check(L.lib.tops_fflayer_step_dp(self.ctx.h, X.b, W.b, b.b, act, dA.b, C.byref(slots[0]), C.byref(slots[1]), C.byref(slots[2]),
+                                                  self._ev if multi else None, self.reserve_sms if multi else 0))
+        if multi:
+            main = torch.cuda.current_stream()
+            self.ctx.check(L.lib.tops_stream_wait_event(self.ctx.h, C.c_void_p(self.comm_stream.cuda_stream), self._ev))
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self.packed_t, op=dist.ReduceOp.SUM, group=self.group)
+            main.wait_stream(self.comm_stream)
+        return (A if A is not None else CuTensor(self.ctx, slots[0]), dX if dX is not None else CuTensor(self.ctx, slots[1]), self.packed)

@@ -418,6 +418,24 @@ def test_host_buffer_entry_point_pipelined(ctx, B, n_chunks):
     assert np.array_equal(packed.numpy(), g)
 
 
+@pytest.mark.parametrize("prec,i,o", [(tb.PREC_F16X3, 784, 10), (tb.PREC_F16X3, 20, 1), (tb.PREC_TF32_BF16X2, 784, 10), (tb.PREC_FP32_SIMT, 96, 72),
+                                      (tb.PREC_FP32_SIMT, 33, 10), (tb.PREC_F16X3, 1024, 1024)])
+def test_host_buffer_entry_point_unfused_db_accumulates(ctx, prec, i, o):
+    """when the forward epilogue cannot fuse the db column sums (o % 4 != 0 such as the MNIST head o = 10 or the Dots head
+    o = 1, FP32_SIMT, the SIMT fallback) the host path must ACCUMULATE db across its row chunks instead of refusing."""
+    ctx.set_precision(prec)
+    rng = np.random.default_rng(i * 131 + o)
+    B = 1500
+    X = rng.uniform(-1, 1, (B, i)).astype(np.float32); dA = rng.normal(size=(B, o)).astype(np.float32)
+    W = rng.normal(0, 0.5, (o, i)).astype(np.float32); b = rng.normal(0, 0.5, o).astype(np.float32)
+    ref = O.fflayer_logistic_dense(X.astype(np.float64), W.astype(np.float64), b.astype(np.float64), dA.astype(np.float64))
+    A = ctx.empty((B, o)); dX = ctx.empty((B, i)); packed = ctx.empty((o * i + o,))
+    g = nn.fflayer_fwd_grad_host(ctx, X, ctx.from_numpy(W), ctx.from_numpy(b), dA, workspace=(A, dX, packed), n_chunks=4)
+    close(A, ref[0], 1e-5, "A"); close(dX, ref[1], 1e-5, "dX")
+    close(g[:o * i].reshape(o, i), ref[2], 1e-5, "dW"); close(g[o * i:], ref[3], 1e-5, "db accumulated over chunks")
+    ctx.set_precision(DEFAULT_PREC)
+
+
 @pytest.mark.parametrize("prec", [tb.PREC_F16X3, tb.PREC_TF32_BF16X2, tb.PREC_TF32X3, tb.PREC_TF32])
 @pytest.mark.parametrize("B", [129, 255, 257, 385, 512])
 def test_cta_pair_tile_edges(ctx, prec, B):
