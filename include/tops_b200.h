@@ -189,6 +189,23 @@ int tops_fflayer_fwd_grad_mc(tops_ctx*, const tops_buf* X, const tops_buf* W, co
  * reference's training fold accumulates one sample at a time (FeedForward.hs:131-148, app/Dots.hs:74-80). */
 int tops_fflayer_step_dp(tops_ctx*, const tops_buf* X, const tops_buf* W, const tops_buf* b, int act, const tops_buf* dA,
                          tops_buf** A, tops_buf** dX, tops_buf** grads, void* grads_ready, int reserve_sms);
+/* ---- recorded graphs: the deferred evaluator of SURVEY 8-b (`tops_graph_begin/op/end/run`), with the API calls themselves as ops.
+ * Between tops_graph_begin and tops_graph_end every call on the context is RECORDED (CUDA stream capture) instead of executed;
+ * buffers allocated meanwhile (results and temporaries) come from the graph's arena (`arena_bytes`, 0 = 64 MiB) and keep their
+ * addresses.  tops_graph_launch replays the whole sequence — the Category-composed forward and reverse sweep of a TOp
+ * (Types.hs:135-157), an SGD step, one sample of trainNetwork's fold (FeedForward.hs:131-148) — as one cudaGraphLaunch, reading
+ * its inputs from and writing its results to the same tensors every time (refresh inputs in place with tops_upload / tops_copy).
+ * Not recordable: anything that reads back to the host (tops_download, tops_index, tops_sync) and the host-buffer entry point.
+ * Tensors returned while recording are views into the arena: they must not outlive tops_graph_destroy. */
+typedef struct tops_graph tops_graph;
+int tops_graph_begin(tops_ctx*, size_t arena_bytes, tops_graph** out);
+int tops_graph_end(tops_ctx*, tops_graph*);
+int tops_graph_launch(tops_ctx*, tops_graph*);
+int64_t tops_graph_kernel_count(const tops_graph*);   /* kernels recorded (what one launch replays) */
+int tops_graph_destroy(tops_ctx*, tops_graph*);
+/* dst <- src, device to device (same dtype and element count): publishes a recorded step's new state into the tensors its next
+ * replay reads, e.g. the SGD-updated parameters of trainNetwork (FeedForward.hs:141-147). */
+int tops_copy(tops_ctx*, tops_buf* dst, const tops_buf* src);
 /* CUDA events for schedules that span streams (the handle is a cudaEvent_t). `stream` NULL = the context's current stream. */
 int tops_event_create(tops_ctx*, void** ev);
 int tops_event_destroy(tops_ctx*, void* ev);

@@ -83,6 +83,12 @@ PROTOTYPES = {
     "tops_fflayer_fwd_grad_host": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p, C.c_int64, c_buf, c_buf, C.c_int, C.c_int, c_bufp, c_bufp, c_bufp, C.c_void_p]),
     "tops_fflayer_fwd_grad_mc": (C.c_int, [c_ctx, c_buf, c_buf, c_buf, C.c_int, c_buf, c_bufp, c_bufp, c_bufp, C.c_void_p]),
     "tops_fflayer_step_dp": (C.c_int, [c_ctx, c_buf, c_buf, c_buf, C.c_int, c_buf, c_bufp, c_bufp, c_bufp, C.c_void_p, C.c_int]),
+    "tops_graph_begin": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "tops_graph_end": (C.c_int, [c_ctx, C.c_void_p]),
+    "tops_graph_launch": (C.c_int, [c_ctx, C.c_void_p]),
+    "tops_graph_kernel_count": (C.c_int64, [C.c_void_p]),
+    "tops_graph_destroy": (C.c_int, [c_ctx, C.c_void_p]),
+    "tops_copy": (C.c_int, [c_ctx, c_buf, c_buf]),
     "tops_event_create": (C.c_int, [c_ctx, C.POINTER(C.c_void_p)]),
     "tops_event_destroy": (C.c_int, [c_ctx, C.c_void_p]),
     "tops_stream_wait_event": (C.c_int, [c_ctx, C.c_void_p, C.c_void_p]),

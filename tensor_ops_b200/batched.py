@@ -214,7 +214,8 @@ def grad_batched(op: TO.TOp, xs: List[BatchT], ds: Optional[List[BatchT]] = None
     if ds is None:
         ref = next(x for x in xs if x.batched).t
         ds = [BatchT(ref.ctx.full((B,), 1.0), True)]
-    gs = op.grad_(BatchT, list(xs), list(ds))
+    with TO.saved_activations():      # forwards of composed prefixes run once per gradient evaluation (top.compose)
+        gs = op.grad_(BatchT, list(xs), list(ds))
     out = []
     for x, g in zip(xs, gs):
         if x.batched:

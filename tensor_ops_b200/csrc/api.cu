@@ -35,6 +35,7 @@ struct tops_ctx {
     int f16x3_fwd_head_kb = 4;    // first two chunks of every tile of the fused forward GEMM (lookahead for its epilogue); TOPS_F16X3_FWD_HEAD
     struct SplitEntry { const void* src; int64_t rows, cols; void* hi; void* lo; long long ld; float* scale2; };
     struct SplitScope* split_scope = nullptr;   // fp16 pairs already made inside the current API call
+    struct tops_graph* capturing = nullptr;     // non-NULL between tops_graph_begin and tops_graph_end: allocations come from its arena
     int64_t launches = 0;
     unsigned int* wd_host = nullptr;
     unsigned int* wd_dev = nullptr;
@@ -43,6 +44,18 @@ struct tops_ctx {
     struct ProfRec { const char* tag; cudaEvent_t e0, e1; double flops, bytes; };
     bool profiling = false;
     std::vector<ProfRec> prof;
+};
+
+// A recorded sequence of API calls (tops_graph_begin .. tops_graph_end) replayed as ONE CUDA graph launch.  Every device buffer
+// allocated while recording — results and temporaries alike — lives in the graph's arena at a fixed address, so a replay writes
+// its results to the same tensors the recording call returned.
+struct tops_graph {
+    tops_ctx* ctx = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    char* arena = nullptr;
+    size_t arena_bytes = 0, used = 0;
+    int64_t launches_recorded = 0;
 };
 
 struct tops_buf {
@@ -119,11 +132,25 @@ int new_buf(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, void* data,
     return TOPS_OK;
 }
 
+int arena_alloc(tops_ctx* ctx, size_t bytes, void** p) {
+    tops_graph* g = ctx->capturing;
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (g->used + need > g->arena_bytes)
+        return set_err(ctx, TOPS_ERR_OOM, "graph arena exhausted: %zu bytes used of %zu, %zu more requested (pass a larger arena to tops_graph_begin)", g->used, g->arena_bytes, need);
+    *p = g->arena + g->used;
+    g->used += need;
+    return TOPS_OK;
+}
+
 int alloc_buf(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, tops_buf** out) {
     int64_t n = 1;
     for (int i = 0; i < rank; ++i) n *= dims[i];
     void* p = nullptr;
     size_t bytes = (size_t)(n > 0 ? n : 1) * esize(dtype);
+    if (ctx->capturing) {   // recording a graph: bump-allocate from its arena (fixed addresses across replays; freed with the graph)
+        TRY(arena_alloc(ctx, bytes, &p));
+        return new_buf(ctx, dtype, rank, dims, p, false, nullptr, out);
+    }
     cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -133,6 +160,15 @@ int alloc_buf(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, tops_buf*
     if (r != TOPS_OK) cudaFreeAsync(p, ctx->stream);
     return r;
 }
+
+// raw workspace for one API call: stream-ordered normally, from the arena while a graph is being recorded
+int ws_alloc(tops_ctx* ctx, size_t bytes, void** p) {
+    if (ctx->capturing) return arena_alloc(ctx, bytes, p);
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(ctx, TOPS_ERR_OOM, "workspace allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); }
+    return TOPS_OK;
+}
+void ws_free(tops_ctx* ctx, void* p) { if (p && !ctx->capturing) cudaFreeAsync(p, ctx->stream); }
 
 void release_buf(tops_buf* b) {
     while (b) {
@@ -357,12 +393,20 @@ extern "C" const char* tops_last_error(tops_ctx* ctx) { return ctx ? ctx->last_e
 
 extern "C" int tops_sync(tops_ctx* ctx) {
     CHECK_CTX(ctx); LOCK(ctx);
+    if (ctx->capturing) return set_err(ctx, TOPS_ERR_INVALID, "a graph is being recorded: calls that read results back to the host (download, index, sync) are not recordable");
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess)
         return set_err(ctx, TOPS_ERR_CUDA, "stream sync failed: %s (gemm watchdog code=0x%x cta=%u)", cudaGetErrorString(e), ctx->wd_host[0], ctx->wd_host[1]);
     return TOPS_OK;
 }
-extern "C" int tops_set_stream(tops_ctx* ctx, void* s) { CHECK_CTX(ctx); LOCK(ctx); ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; return TOPS_OK; }
+extern "C" int tops_set_stream(tops_ctx* ctx, void* s) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (ctx->capturing) return set_err(ctx, TOPS_ERR_INVALID, "tops_set_stream while a graph is being recorded");
+    // work queued on the previous stream may still be using buffers that the next stream's allocations would recycle
+    if (ctx->stream != (s ? (cudaStream_t)s : ctx->own_stream)) cudaStreamSynchronize(ctx->stream);
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return TOPS_OK;
+}
 extern "C" int tops_set_precision(tops_ctx* ctx, int p) {
     CHECK_CTX(ctx); LOCK(ctx);
     if (p < 0 || p > 4) return set_err(ctx, TOPS_ERR_INVALID, "unknown precision %d", p);
@@ -465,6 +509,7 @@ extern "C" int tops_upload(tops_ctx* ctx, tops_buf* dst, const void* host, size_
 extern "C" int tops_download(tops_ctx* ctx, const tops_buf* src, void* host, size_t bytes) {
     CHECK_CTX(ctx); LOCK(ctx);
     if (!src || (!host && bytes)) return set_err(ctx, TOPS_ERR_INVALID, "tops_download: NULL argument");
+    if (ctx->capturing) return set_err(ctx, TOPS_ERR_INVALID, "tops_download is not recordable (it reads back to the host)");
     Tmp tmp; const tops_buf* s;
     TRY(contig(ctx, src, tmp, &s));
     if (bytes != (size_t)s->numel * esize(s->dtype)) return set_err(ctx, TOPS_ERR_SHAPE, "download of %zu bytes from a tensor of %zu bytes", bytes, (size_t)s->numel * esize(s->dtype));
@@ -581,6 +626,7 @@ extern "C" int tops_gemm(tops_ctx* ctx, double alpha, const tops_buf* a, const t
 extern "C" int tops_index(tops_ctx* ctx, const tops_buf* x, const int64_t* idx, double* value) {
     CHECK_CTX(ctx); LOCK(ctx);
     if (!x || !value || (x->rank > 0 && !idx)) return set_err(ctx, TOPS_ERR_INVALID, "tops_index: NULL argument");
+    if (ctx->capturing) return set_err(ctx, TOPS_ERR_INVALID, "tops_index is not recordable (it reads back to the host)");
     int64_t off = 0;
     if (x->tr) {
         if (idx[0] < 0 || idx[0] >= x->dims[0] || idx[1] < 0 || idx[1] >= x->dims[1]) return set_err(ctx, TOPS_ERR_SHAPE, "index out of range");
@@ -810,9 +856,9 @@ extern "C" int tops_sum_rows(tops_ctx* ctx, const tops_buf* x, tops_buf** out) {
     TRY(prep_out(ctx, out, TOPS_F32, s->rank - 1, s->dims + 1));
     if (rows == 0) { k::fill(lc_of(ctx), (float*)(*out)->data, (*out)->numel, 0.f); return check_launch(ctx, "sum_rows"); }
     float* ws = nullptr;
-    CUDA_TRY(ctx, cudaMallocAsync((void**)&ws, sizeof(float) * 64 * (size_t)(cols > 0 ? cols : 1), ctx->stream));
+    TRY(ws_alloc(ctx, sizeof(float) * 64 * (size_t)(cols > 0 ? cols : 1), (void**)&ws));
     k::col_sums(lc_of(ctx), (const float*)s->data, rows, cols, (float*)(*out)->data, ws);
-    cudaFreeAsync(ws, ctx->stream);
+    ws_free(ctx, ws);
     return check_launch(ctx, "sum_rows");
 }
 extern "C" int tops_broadcast_rows(tops_ctx* ctx, int64_t n, const tops_buf* row, tops_buf** out) {
@@ -921,20 +967,20 @@ int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, 
     int* counters = nullptr;
     if (dW_mc) {   // fused all-reduce: region-arrival counters for the "last split pushes the finished region" protocol
         const size_t n = ((size_t)(s.o + 127) / 128 + 1) * ((size_t)(s.i + 127) / 128 + 1) * 8 + 16;   // >= tiles * CTAs per tile * 8 epilogue warps
-        CUDA_TRY(ctx, cudaMallocAsync((void**)&counters, n * sizeof(int), ctx->stream));
+        TRY(ws_alloc(ctx, n * sizeof(int), (void**)&counters));
         CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, n * sizeof(int), ctx->stream));
         g.out0_mc = dW_mc; g.tile_counters = counters;
     }
     int rc_ = run_gemm(ctx, g);
-    if (counters) cudaFreeAsync(counters, ctx->stream);
+    ws_free(ctx, counters);
     TRY(rc_);
     if (db && !db_done) {   // the forward epilogue could not fuse the column sums (rows not 16-byte aligned, FP32_SIMT, SIMT fallback)
         ProfScope prof_(ctx, "col_sums_db", 0.0, (s.dtype == TOPS_BF16 ? 2.0 : 4.0) * (double)s.B * s.o);
         float* ws = nullptr;
-        CUDA_TRY(ctx, cudaMallocAsync((void**)&ws, sizeof(float) * 64 * (size_t)s.o, ctx->stream));
+        TRY(ws_alloc(ctx, sizeof(float) * 64 * (size_t)s.o, (void**)&ws));
         if (s.dtype == TOPS_BF16) k::col_sums_bf16(lc_of(ctx), dZ, s.B, s.o, db, ws, accumulate);
         else k::col_sums(lc_of(ctx), (const float*)dZ, s.B, s.o, db, ws, accumulate);
-        cudaFreeAsync(ws, ctx->stream);
+        ws_free(ctx, ws);
         TRY(check_launch(ctx, "col_sums"));
     }
     return TOPS_OK;
@@ -1024,12 +1070,12 @@ int layer_fwd_grad_f16x3(tops_ctx* ctx, const LayerShapes& s, const void* X, con
         int* counters = nullptr;
         if (dW_mc) {
             const size_t n = ((size_t)(s.o + 127) / 128 + 1) * ((size_t)(s.i + 127) / 128 + 1) * 8 + 16;
-            CUDA_TRY(ctx, cudaMallocAsync((void**)&counters, n * sizeof(int), ctx->stream));
+            TRY(ws_alloc(ctx, n * sizeof(int), (void**)&counters));
             CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, n * sizeof(int), ctx->stream));
             g.out0_mc = dW_mc; g.tile_counters = counters;
         }
         const int rc_ = run_gemm(ctx, g);
-        if (counters) cudaFreeAsync(counters, ctx->stream);
+        ws_free(ctx, counters);
         TRY(rc_);
     }
     if (ev_grads) CUDA_TRY(ctx, cudaEventRecord(ev_grads, ctx->stream));
@@ -1098,6 +1144,7 @@ extern "C" int tops_fflayer_fwd_grad_host(tops_ctx* ctx, const float* X_host, co
                                           int act, int n_chunks, tops_buf** A, tops_buf** dX, tops_buf** grads, float* grads_host) {
     CHECK_CTX(ctx); LOCK(ctx);
     if (!X_host || !dA_host || !W || !grads || B < 0) return set_err(ctx, TOPS_ERR_INVALID, "fflayer_fwd_grad_host: NULL argument");
+    if (ctx->capturing) return set_err(ctx, TOPS_ERR_INVALID, "the host-buffer entry point is not recordable (it uses its own copy stream)");
     if (W->rank != 2 || W->dtype != TOPS_F32 || W->tr || (b && (b->rank != 1 || b->dims[0] != W->dims[0] || b->dtype != TOPS_F32)))
         return set_err(ctx, TOPS_ERR_SHAPE, "fflayer_fwd_grad_host: W[o,i] b[o] fp32 expected");
     TRY(check_act(ctx, act));
@@ -1200,6 +1247,69 @@ extern "C" int tops_fflayer_fwd_grad_mc(tops_ctx* ctx, const tops_buf* X, const 
     k::mc_push(lc_of(ctx), db, db_mc, s.o);            // o floats: the bias gradient joins the same multicast buffer
     TRY(check_launch(ctx, "mc_push"));
     if (dX) TRY(dx_gemm(ctx, s, dZ->data, W->data, (*dX)->data, EPI_STORE, ACT_ID, nullptr, nullptr, nullptr, &ws));
+    return TOPS_OK;
+}
+
+// ================================================================================================ recorded graphs
+// The deferred evaluator SURVEY 8-b sketches (`tops_graph_begin/op/end/run`): instead of a separate op vocabulary, the API calls
+// themselves are the ops.  Between begin and end every call is recorded (CUDA stream capture on the context's stream) instead of
+// executed; tops_graph_launch replays the whole sequence — a composed TOp's forward and reverse sweep, an SGD step, a per-sample
+// training step — as ONE cudaGraphLaunch: no per-method launch latency, no host round-trip between the Category-composed stages.
+// Inputs are read from, and results written to, the same tensors on every replay (update inputs in place with tops_upload /
+// tops_copy before launching).
+extern "C" int tops_graph_begin(tops_ctx* ctx, size_t arena_bytes, tops_graph** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!out) return set_err(ctx, TOPS_ERR_INVALID, "tops_graph_begin: NULL slot");
+    if (ctx->capturing) return set_err(ctx, TOPS_ERR_INVALID, "tops_graph_begin: already recording");
+    if (ctx->profiling) return set_err(ctx, TOPS_ERR_INVALID, "tops_graph_begin: switch per-kernel profiling off first");
+    tops_graph* g = new tops_graph();
+    g->ctx = ctx; g->arena_bytes = arena_bytes ? arena_bytes : ((size_t)64 << 20);
+    if (cudaMalloc((void**)&g->arena, g->arena_bytes) != cudaSuccess) { cudaGetLastError(); delete g; return set_err(ctx, TOPS_ERR_OOM, "graph arena of %zu bytes", arena_bytes); }
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaFree(g->arena); delete g; return set_err(ctx, TOPS_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e)); }
+    g->launches_recorded = ctx->launches;
+    ctx->capturing = g;
+    *out = g;
+    return TOPS_OK;
+}
+extern "C" int tops_graph_end(tops_ctx* ctx, tops_graph* g) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!g || ctx->capturing != g) return set_err(ctx, TOPS_ERR_INVALID, "tops_graph_end: not the graph being recorded");
+    ctx->capturing = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
+    if (e != cudaSuccess || !g->graph) { cudaGetLastError(); return set_err(ctx, TOPS_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e)); }
+    e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess) return set_err(ctx, TOPS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    g->launches_recorded = ctx->launches - g->launches_recorded;
+    return TOPS_OK;
+}
+extern "C" int tops_graph_launch(tops_ctx* ctx, tops_graph* g) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!g || !g->exec) return set_err(ctx, TOPS_ERR_INVALID, "tops_graph_launch: graph not finished");
+    CUDA_TRY(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->launches_recorded;
+    return TOPS_OK;
+}
+extern "C" int64_t tops_graph_kernel_count(const tops_graph* g) { return g ? g->launches_recorded : -1; }
+extern "C" int tops_graph_destroy(tops_ctx* ctx, tops_graph* g) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!g) return TOPS_OK;
+    if (ctx->capturing == g) { cudaGraph_t tmp = nullptr; cudaStreamEndCapture(ctx->stream, &tmp); if (tmp) cudaGraphDestroy(tmp); ctx->capturing = nullptr; cudaGetLastError(); }
+    cudaStreamSynchronize(ctx->stream);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    if (g->arena) cudaFree(g->arena);
+    delete g;
+    return TOPS_OK;
+}
+// dst <- src (same element count and dtype), device to device: how a recorded step publishes its new state (e.g. the SGD-updated
+// parameters) into the tensors its next replay reads
+extern "C" int tops_copy(tops_ctx* ctx, tops_buf* dst, const tops_buf* src) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    if (!dst || !src) return set_err(ctx, TOPS_ERR_INVALID, "tops_copy: NULL tensor");
+    if (dst->tr || src->tr) return set_err(ctx, TOPS_ERR_INVALID, "tops_copy: transposed views are not accepted");
+    if (dst->dtype != src->dtype || dst->numel != src->numel) return set_err(ctx, TOPS_ERR_SHAPE, "tops_copy: %lld elements of dtype %d into %lld of dtype %d", (long long)src->numel, src->dtype, (long long)dst->numel, dst->dtype);
+    if (src->numel) CUDA_TRY(ctx, cudaMemcpyAsync(dst->data, src->data, (size_t)src->numel * esize(src->dtype), cudaMemcpyDeviceToDevice, ctx->stream));
     return TOPS_OK;
 }
 

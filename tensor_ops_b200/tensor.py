@@ -43,6 +43,10 @@ class Context:
     def sm_count(self) -> int: return L.lib.tops_device_sm_count(self.h)
     def profile(self, on: bool): self.check(L.lib.tops_profile_enable(self.h, int(on)))
 
+    def record(self, arena_bytes: int = 64 << 20) -> "Graph":
+        """`with ctx.record() as g: ...` records every library call of the block into a graph (tops_graph_*); `g.launch()` replays it."""
+        return Graph(self, arena_bytes)
+
     def profile_summary(self) -> dict:
         """Per-tag device times of the launches since profiling was enabled (synchronises)."""
         import json
@@ -106,6 +110,40 @@ class Context:
         assert t.is_cuda and t.is_contiguous()
         dt = {torch.float32: L.F32, torch.bfloat16: L.BF16}[t.dtype]
         return self.wrap(t.data_ptr(), tuple(t.shape), dt, keepalive=t)
+
+
+class Graph:
+    """A recorded sequence of library calls replayed as one CUDA graph launch (tops_graph_begin/end/launch): the deferred,
+    on-device evaluation of a composed TOp pipeline — forward, reverse sweep, parameter update — without per-method launch latency.
+    Tensors created inside the `with` block live in the graph's arena: keep the Graph alive while they are used."""
+
+    def __init__(self, ctx: Context, arena_bytes: int = 64 << 20):
+        self.ctx, self.arena_bytes, self.h = ctx, int(arena_bytes), None
+
+    def __enter__(self):
+        h = C.c_void_p()
+        self.ctx.check(L.lib.tops_graph_begin(self.ctx.h, self.arena_bytes, C.byref(h)))
+        self.h = h
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is not None:               # abandon the recording
+            L.lib.tops_graph_destroy(self.ctx.h, self.h)
+            self.h = None
+            return False
+        self.ctx.check(L.lib.tops_graph_end(self.ctx.h, self.h))
+        return False
+
+    def launch(self):
+        self.ctx.check(L.lib.tops_graph_launch(self.ctx.h, self.h))
+
+    def kernel_count(self) -> int:
+        return int(L.lib.tops_graph_kernel_count(self.h))
+
+    def close(self):
+        if self.h is not None:
+            self.ctx.check(L.lib.tops_graph_destroy(self.ctx.h, self.h))
+            self.h = None
 
 
 _default: Optional[Context] = None
@@ -184,6 +222,11 @@ class CuTensor:
         self.ctx.check(L.lib.tops_upload(self.ctx.h, self.b, host.ctypes.data_as(C.c_void_p), host.nbytes))
         if sync:
             self.ctx.sync()
+        return self
+
+    def copy_from(self, src: "CuTensor") -> "CuTensor":
+        """this tensor's storage <- src (device to device, tops_copy): how a recorded step publishes new state in place."""
+        self.ctx.check(L.lib.tops_copy(self.ctx.h, self.b, src.b))
         return self
 
     def download_into(self, host: np.ndarray) -> np.ndarray:

@@ -43,24 +43,66 @@ def runTOp(o: TOp, xs: Prod, T=None) -> Prod:
     return o.run(_T(xs, T), list(xs))
 
 
+# Saved activations.  The reference's chain rule `g3 xs ds = g1 xs (g2 (f1 xs) ds)` (Types.hs:155) re-runs the forward of every
+# prefix inside the gradient: a composition of n ops evaluates O(n^2) forwards (every `>>>` nests another `f1 xs`).  Tensors are
+# immutable values, so within ONE gradient evaluation the forward of a composed prefix on the same input objects is the same
+# value: `compose` looks it up here instead of launching it again — the reverse sweep then costs n forwards + n VJPs, the
+# saved-activations schedule, with results identical to the reference's (same kernels on the same inputs, just not repeated).
+_saved: Optional[dict] = None
+forward_evals = 0          # instrumentation for the tests: forwards of composed prefixes actually executed
+
+
+class saved_activations:
+    """Scope in which forwards of composed prefixes are memoised (entered by gradTOp / gradTOp_; re-entrant)."""
+
+    def __enter__(self):
+        global _saved
+        self.outer = _saved
+        if _saved is None:
+            _saved = {}
+        return self
+
+    def __exit__(self, *exc):
+        global _saved
+        _saved = self.outer
+        return False
+
+
+def _run_saved(o: "TOp", T, xs: Prod) -> Prod:
+    global forward_evals
+    if _saved is None:
+        forward_evals += 1
+        return o.run(T, xs)
+    key = (id(o), id(T)) + tuple(id(x) for x in xs)
+    hit = _saved.get(key)
+    if hit is None:
+        forward_evals += 1
+        hit = (o.run(T, xs), o, list(xs))      # o and xs are kept alive so that their ids cannot be recycled inside the scope
+        _saved[key] = hit
+    return list(hit[0])
+
+
 def gradTOp_(o: TOp, xs: Prod, ds: Prod, T=None) -> Prod:
     """`gradTOp'` (Types.hs:124)."""
-    return o.grad_(_T(xs, T), list(xs), list(ds))
+    with saved_activations():
+        return o.grad_(_T(xs, T), list(xs), list(ds))
 
 
 def gradTOp(o: TOp, xs: Prod, T=None) -> Prod:
     """`gradTOp` (Types.hs:127-132): cotangent of the scalar output seeded with 1."""
     T = _T(xs, T)
-    return o.grad_(T, list(xs), [T.konst((), 1.0, xs[0])])
+    with saved_activations():
+        return o.grad_(T, list(xs), [T.konst((), 1.0, xs[0])])
 
 
 # ------------------------------------------------------------------ Category / routing (Types.hs:135-264)
 def compose(o2: TOp, o1: TOp) -> TOp:
-    """`(.)`: g3 xs ds = g1 xs (g2 (f1 xs) ds)  (Types.hs:141-157).  The forward of o1 is re-evaluated inside the
-    gradient as in the reference; the batched backend memoises it so no GEMM runs twice."""
+    """`(.)`: g3 xs ds = g1 xs (g2 (f1 xs) ds)  (Types.hs:141-157).  The reference re-evaluates `f1 xs` inside the gradient;
+    here that forward is taken from the saved activations of the enclosing gradient evaluation when it has already run
+    (see `saved_activations`), so a chain of n ops costs O(n) launches instead of O(n^2)."""
     assert o1.n_out == o2.n_in, f"cannot compose: {o1.n_out} outputs into {o2.n_in} inputs"
-    return TOp(lambda T, xs: o2.run(T, o1.run(T, xs)),
-               lambda T, xs, ds: o1.grad_(T, xs, o2.grad_(T, o1.run(T, xs), ds)),
+    return TOp(lambda T, xs: o2.run(T, _run_saved(o1, T, xs)),
+               lambda T, xs, ds: o1.grad_(T, xs, o2.grad_(T, _run_saved(o1, T, xs), ds)),
                o1.n_in, o2.n_out, ("seq", o1.tag, o2.tag))
 
 

@@ -83,3 +83,28 @@ def test_gmul_vjp_matches_oracle_for_rank3():
     got = TO.gradTOp_(TO.gmul(1, 2, 1), [NpT(x), NpT(y)], [NpT(ct)])
     for g, w in zip(got, want):
         np.testing.assert_allclose(g.a, w, rtol=1e-12)
+
+
+def test_saved_activations_make_a_chain_linear_in_forwards():
+    """`g3 xs ds = g1 xs (g2 (f1 xs) ds)` (Types.hs:155) nests a forward of the prefix in every `>>>`; with the
+    saved-activations scope a chain of n ops runs each composed prefix ONCE per gradient evaluation, and the values are the
+    reference's (checked against the oracle's own, un-memoised, chain rule)."""
+    from oracle import tensor_ops_oracle as O
+    from nptensor import NpT
+    rng = np.random.default_rng(3)
+    n = 12
+    x = NpT(rng.uniform(0.2, 1.5, 5))
+    op, oop = TO.scale(1.1), O.op_scale(1.1)
+    for k in range(n - 1):
+        op = op >> TO.scale(1.0 + 0.01 * k) if k % 2 else op >> TO.map(lambda v: 0.25 * v * v + 0.5)
+        oop = oop >> O.op_scale(1.0 + 0.01 * k) if k % 2 else oop >> O.op_map(lambda v: 0.25 * v * v + 0.5)
+    ct = NpT(rng.normal(size=5))
+    TO.forward_evals = 0
+    (g,) = TO.gradTOp_(op, [x], [ct])
+    linear = TO.forward_evals
+    assert linear <= n, linear                      # one forward per composed prefix
+    np.testing.assert_allclose(g.a, O.gradTOp_(oop, [x.a], [ct.a])[0], rtol=1e-12)
+    # without the scope the same call tree re-runs every prefix at every level: quadratic
+    TO.forward_evals = 0
+    op.grad_(NpT, [x], [ct])
+    assert TO.forward_evals >= n * (n - 1) // 2, TO.forward_evals

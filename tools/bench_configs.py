@@ -26,6 +26,11 @@ def timeit(fn, steps=10, warm=3):
     return wall, {k: v["ms"] / v["launches"] * (v["launches"] / steps) for k, v in prof.items()}
 
 
+only = None
+if "--prec" in sys.argv:            # e.g. --prec f16x3: one precision only (used under ncu)
+    k = sys.argv.index("--prec"); only = sys.argv[k + 1]; del sys.argv[k:k + 2]
+PRECS_ALL = ((tb.PREC_F16X3, "f16x3"), (tb.PREC_TF32_BF16X2, "tf32bf16"), (tb.PREC_TF32X3, "tf32x3"), (tb.PREC_TF32, "tf32"), (tb.PREC_FP32_SIMT, "simt"))
+def precs(names): return [(p, n) for p, n in PRECS_ALL if n in names and (only is None or n == only)]
 which = set(sys.argv[1:]) or {"3", "4", "5"}
 if "3" in which:
     B, dims = 32768, [784, 512, 256, 10]
@@ -35,7 +40,7 @@ if "3" in which:
     Yh = np.zeros((B, 10), np.float32); Yh[np.arange(B), np.random.default_rng(0).integers(0, 10, B)] = 1
     Y = ctx.from_numpy(Yh)
     acts = [L.ACT_LOGISTIC, L.ACT_LOGISTIC, L.ACT_SOFTMAX]
-    for prec, name in ((tb.PREC_TF32_BF16X2, "tf32bf16"), (tb.PREC_TF32X3, "tf32x3"), (tb.PREC_TF32, "tf32")):
+    for prec, name in precs(("f16x3", "tf32bf16", "tf32x3", "tf32")):
         ctx.set_precision(prec)
         ms, per = timeit(lambda: nn.mlp_fwd_grad(Ws, bs, acts, L.LOSS_CROSS_ENTROPY, X, Y))
         flop = 6.0 * B * (784 * 512 + 512 * 256 + 256 * 10)
@@ -56,7 +61,7 @@ if "5" in which:
     rng = np.random.default_rng(5)
     x = ctx.from_numpy(rng.normal(size=(64, 64, 64))); y = ctx.from_numpy(rng.normal(size=(64, 64))); d = ctx.from_numpy(rng.normal(size=(64, 64)))
     op = TO.compose(TO.sumRows(), TO.inner(2, 1))      # inner (LS (LS LZ)) (LS LZ) >>> sumRows   (SURVEY §8-d note on config 5)
-    for prec, name in ((tb.PREC_TF32_BF16X2, "tf32bf16"), (tb.PREC_TF32X3, "tf32x3"), (tb.PREC_FP32_SIMT, "simt")):
+    for prec, name in precs(("f16x3", "tf32bf16", "tf32x3", "simt")):
         ctx.set_precision(prec)
         def step():
             TO.runTOp(op, [x, y]); TO.gradTOp_(op, [x, y], [d])

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
-tail -6 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -5 gpurun_out/bench.err; cat gpurun_out/bench.json
+timeout 900 python -m pytest tests/test_gpu_graph.py tests/test_recurrent.py -m gpu -q -x --timeout 600 > gpurun_out/pytest_graph.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_graph.log
+tail -25 gpurun_out/pytest_graph.log
