@@ -149,6 +149,12 @@ enum {
  *   z[m..,n..] = sum_{o..} x[m..,o..] * y[reverse(o..),n..].   Replaces BTensor.gmulB/gmulBLAS/naiveGMul
  *   (Backend/BTensor.hs:592-716) with one tensor-core GEMM on flat storage (plus an axis permutation when |os|>=2). */
 int tops_gmul(tops_ctx*, int len_m, int len_o, int len_n, const tops_buf* x, const tops_buf* y, tops_buf** out);
+/* `gmul lM lO lN >>> sumRows` (TOp.hs:56-94,151-159) as one primitive and its VJP — the fusion the deferred evaluator applies when it
+ * meets that composition: sumRows (gmul x y) = gmul (sumRows x) y, so the [A, ...] intermediate is never formed (the reference
+ * computes A separate gemms through mapBTM, BTensor.hs:706-710, then adds them).  out: dims ms[1..] ++ ns.  VJP: ct has out's shape;
+ * dx = x's shape (the cotangent broadcast over the summed axis, contracted with y), dy = y's shape. */
+int tops_gmul_sum_rows(tops_ctx*, int lM, int lO, int lN, const tops_buf* x, const tops_buf* y, tops_buf** out);
+int tops_gmul_sum_rows_vjp(tops_ctx*, int lM, int lO, int lN, const tops_buf* x, const tops_buf* y, const tops_buf* ct, tops_buf** dx, tops_buf** dy);
 int tops_sum_t(tops_ctx*, int n, const tops_buf* const* xs, tops_buf** out);                                  /* sumT Types.hs:69 (left fold, in order) */
 int tops_sum_rows(tops_ctx*, const tops_buf* x, tops_buf** out);                                              /* sumRows Types.hs:82-84 */
 int tops_broadcast_rows(tops_ctx*, int64_t n, const tops_buf* row, tops_buf** out);                           /* mapRows (LS LZ) (const row): VJP of sumRows, TOp.hs:151-159 */

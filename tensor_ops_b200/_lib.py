@@ -71,6 +71,8 @@ PROTOTYPES = {
     "tops_sum": (C.c_int, [c_ctx, c_buf, c_bufp]),
     "tops_lift": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, c_bufp, C.c_int, c_i64p, c_bufp]),
     "tops_gmul": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, c_buf, c_buf, c_bufp]),
+    "tops_gmul_sum_rows": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, c_buf, c_buf, c_bufp]),
+    "tops_gmul_sum_rows_vjp": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, c_buf, c_buf, c_buf, c_bufp, c_bufp]),
     "tops_sum_t": (C.c_int, [c_ctx, C.c_int, c_bufp, c_bufp]),
     "tops_sum_rows": (C.c_int, [c_ctx, c_buf, c_bufp]),
     "tops_broadcast_rows": (C.c_int, [c_ctx, C.c_int64, c_buf, c_bufp]),

@@ -291,7 +291,11 @@ int run_gemm_f16x3(tops_ctx* ctx, const GemmCall& c0) {
 int run_gemm(tops_ctx* ctx, GemmCall c) {
     if (c.colsum_fused) *c.colsum_fused = 0;
     if (c.M <= 0 || c.N <= 0) return TOPS_OK;
-    if (c.dtype == 0 && ctx->precision == TOPS_PREC_F16X3) {   // fp32 operands become fp16 pairs; comes back here with dtype 2
+    // F16X3 with fp32 operands: split them into fp16 pairs (comes back here with dtype 2).  Small products (< 2 GFLOP) are not worth
+    // the split passes: they take the in-kernel TF32 + bf16-correction route below when TMA can describe them as they are.
+    const bool f16x3 = c.dtype == 0 && ctx->precision == TOPS_PREC_F16X3;
+    const bool small = 2.0 * c.M * c.N * (double)c.K < 2147483648.0;
+    if (f16x3 && !small) {
         const int r = run_gemm_f16x3(ctx, c);
         if (r != kF16X3Fallback) return r;
     }
@@ -313,6 +317,11 @@ int run_gemm(tops_ctx* ctx, GemmCall c) {
         int r = gemm_umma_launch(c, ctx->stream, ctx->wd_dev, ctx->num_sms, err, sizeof err);
         if (r == 0) { ++ctx->launches; return TOPS_OK; }
         if (r > 0) return set_err(ctx, TOPS_ERR_CUDA, "%s", err);
+        if (f16x3 && small && c.K > 0) {   // rows TMA cannot describe (e.g. 10 columns): the split pads them, so the tensor cores still apply
+            if (c.epi == EPI_ATOMIC) c.accumulate = 1;   // already zeroed above
+            const int r2 = run_gemm_f16x3(ctx, c);
+            if (r2 != kF16X3Fallback) return r2;
+        }
         if (c.dtype != 0) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "16-bit gemm needs 16-byte aligned operands with strides that are multiples of 8 elements (%s)", err);
     }
     if (c.out0_mc) return set_err(ctx, TOPS_ERR_UNSUPPORTED, "the fused all-reduce needs the tcgen05 GEMM: 16-byte aligned operands and rows");
@@ -818,6 +827,73 @@ extern "C" int tops_gmul(tops_ctx* ctx, int lM, int lO, int lN, const tops_buf* 
     g.epi = EPI_STORE; g.alpha = 1.f; g.beta = 0.f; g.out0 = o; g.ld_out0 = N; g.tag = "gmul";
     split_k_if_skinny(ctx, g);
     return run_gemm(ctx, g);
+}
+
+// `gmul lM lO lN >>> sumRows` as one primitive (a fusion the deferred evaluator applies to the composed TOp, top.py): the row sum
+// commutes with the contraction, so  sumRows (gmul x y) = gmul (sumRows x) y  and the [A, ...] intermediate is never formed.
+//   lO == 1, small y: ONE pass over x (k_gsr_fwd).   Otherwise: sum_rows + gmul on the reduced operand.
+namespace {
+bool gsr_shapes(tops_ctx* ctx, int lM, int lO, int lN, const tops_buf* x, const tops_buf* y, int64_t* A, int64_t* R, int64_t* K, int64_t* N) {
+    if (lO != 1 || x->tr || y->tr || x->numel == 0 || y->numel == 0) return false;
+    *A = x->dims[0]; *R = 1; *N = 1;
+    for (int i = 1; i < lM; ++i) *R *= x->dims[i];
+    *K = x->dims[lM];
+    for (int i = 0; i < lN; ++i) *N *= y->dims[lO + i];
+    return k::gsr_fits(*K, *N) && *R < (1ll << 31);
+}
+int gsr_check(tops_ctx* ctx, int lM, int lO, int lN, const tops_buf* x, const tops_buf* y) {
+    TRY(need_f32(ctx, x, "tops_gmul_sum_rows")); TRY(need_f32(ctx, y, "tops_gmul_sum_rows"));
+    if (lM < 1 || lO < 0 || lN < 0 || x->rank != lM + lO || y->rank != lO + lN || lM - 1 + lN > TOPS_MAX_RANK)
+        return set_err(ctx, TOPS_ERR_SHAPE, "gmul_sum_rows: ranks %d,%d do not match |ms|=%d (>= 1) |os|=%d |ns|=%d", x->rank, y->rank, lM, lO, lN);
+    for (int i = 0; i < lO; ++i)
+        if (x->dims[lM + i] != y->dims[lO - 1 - i]) return set_err(ctx, TOPS_ERR_SHAPE, "gmul_sum_rows: contraction dimension %d differs", i);
+    return TOPS_OK;
+}
+}  // namespace
+
+extern "C" int tops_gmul_sum_rows(tops_ctx* ctx, int lM, int lO, int lN, const tops_buf* x, const tops_buf* y, tops_buf** out) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(gsr_check(ctx, lM, lO, lN, x, y));
+    int64_t A, R, K, N;
+    if (gsr_shapes(ctx, lM, lO, lN, x, y, &A, &R, &K, &N)) {
+        int64_t od[TOPS_MAX_RANK];
+        for (int i = 1; i < lM; ++i) od[i - 1] = x->dims[i];
+        for (int i = 0; i < lN; ++i) od[lM - 1 + i] = y->dims[lO + i];
+        TRY(prep_out(ctx, out, TOPS_F32, lM - 1 + lN, od));
+        ProfScope prof_(ctx, "gmul_sum_rows", 2.0 * R * K * N, 4.0 * ((double)x->numel + y->numel + R * N));
+        k::gsr_fwd(lc_of(ctx), (const float*)x->data, (const float*)y->data, (float*)(*out)->data, A, R, (int)K, (int)N);
+        return check_launch(ctx, "gmul_sum_rows");
+    }
+    tops_buf* xs = nullptr;
+    TRY(tops_sum_rows(ctx, x, &xs));
+    Tmp tmp; tmp.keep(xs);
+    return tops_gmul(ctx, lM - 1, lO, lN, xs, y, out);
+}
+
+extern "C" int tops_gmul_sum_rows_vjp(tops_ctx* ctx, int lM, int lO, int lN, const tops_buf* x, const tops_buf* y, const tops_buf* ct,
+                                      tops_buf** dx, tops_buf** dy) {
+    CHECK_CTX(ctx); LOCK(ctx);
+    TRY(gsr_check(ctx, lM, lO, lN, x, y));
+    TRY(need_f32(ctx, ct, "tops_gmul_sum_rows_vjp"));
+    if (!dx || !dy) return set_err(ctx, TOPS_ERR_INVALID, "gmul_sum_rows_vjp: NULL output slot");
+    int64_t A, R, K, N;
+    if (gsr_shapes(ctx, lM, lO, lN, x, y, &A, &R, &K, &N) && !ct->tr) {
+        if (ct->numel != R * N) return set_err(ctx, TOPS_ERR_SHAPE, "gmul_sum_rows_vjp: cotangent has %lld elements, expected %lld", (long long)ct->numel, (long long)(R * N));
+        TRY(prep_out(ctx, dx, TOPS_F32, x->rank, x->dims));
+        TRY(prep_out(ctx, dy, TOPS_F32, y->rank, y->dims));
+        ProfScope prof_(ctx, "gmul_sum_rows_vjp", 4.0 * R * K * N, 4.0 * (2.0 * x->numel + 2.0 * y->numel + R * N));
+        CUDA_TRY(ctx, cudaMemsetAsync((*dy)->data, 0, sizeof(float) * (size_t)(K * N), ctx->stream));
+        k::gsr_vjp(lc_of(ctx), (const float*)x->data, (const float*)y->data, (const float*)ct->data, (float*)(*dx)->data, (float*)(*dy)->data, A, R, (int)K, (int)N);
+        return check_launch(ctx, "gmul_sum_rows_vjp");
+    }
+    // general shapes: the reference's own VJP chain (TOp.hs:73-93,151-159) on the existing primitives
+    Tmp tmp;
+    tops_buf *dz = nullptr, *yt = nullptr, *xt = nullptr;
+    TRY(tops_broadcast_rows(ctx, x->dims[0], ct, &dz)); tmp.keep(dz);
+    TRY(tops_transp(ctx, y, &yt)); tmp.keep(yt);
+    TRY(tops_transp(ctx, x, &xt)); tmp.keep(xt);
+    TRY(tops_gmul(ctx, lM, lN, lO, dz, yt, dx));
+    return tops_gmul(ctx, lO, lM, lN, xt, dz, dy);
 }
 
 extern "C" int tops_sum_t(tops_ctx* ctx, int n, const tops_buf* const* xs, tops_buf** out) {

@@ -476,6 +476,123 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const float* __restrict__ A, 
 
 }  // namespace
 
+// ---------------------------------------------------------------------- contraction followed by sumRows, fused
+// out[r,n] = sum_a sum_k x[a,r,k] y[k,n]  ==  (sum_a x[a,r,:]) . y      — `gmul lM 1 lN >>> sumRows` (TOp.hs:56-94,151-159) as ONE pass
+// over x: the row sum commutes with the contraction, so the [A,R,N] intermediate of the reference (64 separate 64^3 gemms at
+// BASELINE configs[4]) is never formed.  One CTA per r; K*(N+1) floats of y staged in shared memory by the VJP.
+constexpr int kGsrThreads = 512;
+
+__global__ void __launch_bounds__(kGsrThreads) k_gsr_fwd(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                                         int64_t A, int64_t R, int K, int N) {
+    extern __shared__ float sh[];                 // [groups][K] partial row sums, then xs[K] in sh[0..K)
+    const int r = blockIdx.x, t = threadIdx.x;
+    const int KT = K < kGsrThreads ? K : kGsrThreads;      // threads along k
+    const int groups = kGsrThreads / KT;                    // thread groups along a
+    const int g = t / KT, kk = t % KT;
+    for (int k0 = 0; k0 < K; k0 += KT) {
+        const int k = k0 + kk;
+        float acc = 0.f;
+        if (g < groups && k < K) {
+            const float* p = x + ((int64_t)g * R + r) * K + k;
+            const int64_t step = (int64_t)groups * R * K;
+            int64_t a = g;
+            for (; a + 7 * groups < A; a += 8 * groups, p += 8 * step) {      // 8 independent loads in flight per thread
+                const float v0 = __ldg(p), v1 = __ldg(p + step), v2 = __ldg(p + 2 * step), v3 = __ldg(p + 3 * step);
+                const float v4 = __ldg(p + 4 * step), v5 = __ldg(p + 5 * step), v6 = __ldg(p + 6 * step), v7 = __ldg(p + 7 * step);
+                acc += ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+            }
+            for (; a < A; a += groups, p += step) acc += __ldg(p);
+            sh[g * K + k] = acc;
+        }
+    }
+    __syncthreads();
+    for (int k = t; k < K; k += kGsrThreads) {
+        float s = sh[k];
+        for (int gg = 1; gg < groups; ++gg) s += sh[gg * K + k];
+        sh[k] = s;
+    }
+    __syncthreads();
+    for (int n = t; n < N; n += kGsrThreads) {
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(sh[k], __ldg(y + (int64_t)k * N + n), acc);
+        out[(int64_t)r * N + n] = acc;
+    }
+}
+
+// VJP with cotangent ct[R,N]:  dx[a,r,k] = sum_n ct[r,n] y[k,n]  (the same for every a: written A times, never materialising the
+// broadcast cotangent),  dy[k,n] += (sum_a x[a,r,k]) ct[r,n]  (rank-1 update per r, fp32 reds into the pre-zeroed dy).
+template <int PER>   // PER > 0: dy partials of RB rows kept in PER registers per thread (K*N <= PER * threads); 0: one red per row and entry
+__global__ void __launch_bounds__(kGsrThreads) k_gsr_vjp(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ ct,
+                                                         float* __restrict__ dx, float* __restrict__ dy, int64_t A, int64_t R, int K, int N, int RB) {
+    extern __shared__ float sh[];
+    float* ys = sh;                               // [K][N+1] (padded: a thread per k walks n)
+    float* cts = ys + (size_t)K * (N + 1);        // [N]
+    float* tk = cts + N;                          // [K]   t[k] = sum_n ct[r,n] y[k,n]
+    float* xs = tk + K;                           // [groups][K] -> xs[K]
+    const int t = threadIdx.x;
+    for (int i = t; i < K * N; i += kGsrThreads) ys[(i / N) * (N + 1) + (i % N)] = __ldg(y + i);
+    const int KT = K < kGsrThreads ? K : kGsrThreads;
+    const int groups = kGsrThreads / KT;
+    const int g = t / KT, kk = t % KT;
+    float part[PER > 0 ? PER : 1];
+#pragma unroll
+    for (int j = 0; j < (PER > 0 ? PER : 1); ++j) part[j] = 0.f;
+    const int64_t r_end = min(R, (int64_t)(blockIdx.x + 1) * RB);
+    for (int64_t r = (int64_t)blockIdx.x * RB; r < r_end; ++r) {
+        __syncthreads();                          // previous row's xs / cts / tk fully consumed (and ys loaded, first time)
+        for (int n = t; n < N; n += kGsrThreads) cts[n] = __ldg(ct + r * N + n);
+        for (int k0 = 0; k0 < K; k0 += KT) {      // row sums of x over a (needed by dy), coalesced along k
+            const int k = k0 + kk;
+            float acc = 0.f;
+            if (g < groups && k < K) {
+                const float* p = x + ((int64_t)g * R + r) * K + k;
+                const int64_t step = (int64_t)groups * R * K;
+                int64_t a = g;
+                for (; a + 7 * groups < A; a += 8 * groups, p += 8 * step) {
+                    const float v0 = __ldg(p), v1 = __ldg(p + step), v2 = __ldg(p + 2 * step), v3 = __ldg(p + 3 * step);
+                    const float v4 = __ldg(p + 4 * step), v5 = __ldg(p + 5 * step), v6 = __ldg(p + 6 * step), v7 = __ldg(p + 7 * step);
+                    acc += ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+                }
+                for (; a < A; a += groups, p += step) acc += __ldg(p);
+                xs[g * K + k] = acc;
+            }
+        }
+        __syncthreads();
+        for (int k = t; k < K; k += kGsrThreads) {
+            float s = xs[k];
+            for (int gg = 1; gg < groups; ++gg) s += xs[gg * K + k];
+            xs[k] = s;
+            float acc = 0.f;
+            for (int n = 0; n < N; ++n) acc = fmaf(cts[n], ys[k * (N + 1) + n], acc);
+            tk[k] = acc;
+        }
+        __syncthreads();
+        for (int k0 = 0; k0 < K; k0 += KT) {      // dx: A copies of t[k], coalesced along k
+            const int k = k0 + kk;
+            if (g < groups && k < K) {
+                const float v = tk[k];
+                for (int64_t a = g; a < A; a += groups) dx[(a * R + r) * K + k] = v;
+            }
+        }
+        if constexpr (PER > 0) {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int i = t + j * kGsrThreads;
+                if (i < K * N) part[j] = fmaf(xs[i / N], cts[i % N], part[j]);
+            }
+        } else {
+            for (int i = t; i < K * N; i += kGsrThreads) atomicAdd(dy + i, xs[i / N] * cts[i % N]);
+        }
+    }
+    if constexpr (PER > 0) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = t + j * kGsrThreads;
+            if (i < K * N) atomicAdd(dy + i, part[j]);
+        }
+    }
+}
+
 // ====================================================================== launch wrappers
 namespace {
 __global__ void k_mc_push(const float* __restrict__ src, float* out_mc, int64_t n) {
@@ -502,6 +619,31 @@ __global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restr
 void split_bf16(const LaunchCtx& lc, const float* x, void* v, void* lo, int64_t n) {
     if (n <= 0) return;
     k_split_bf16<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(x, (__nv_bfloat16*)v, (__nv_bfloat16*)lo, n);
+    count(lc);
+}
+
+size_t gsr_vjp_smem(int K, int N) { return sizeof(float) * ((size_t)K * (N + 1) + N + K + (size_t)(kGsrThreads / (K < kGsrThreads ? K : kGsrThreads)) * K); }
+bool gsr_fits(int64_t K, int64_t N) { return K >= 1 && N >= 1 && K <= 1024 && N <= 4096 && gsr_vjp_smem((int)K, (int)N) <= 96 * 1024; }
+void gsr_fwd(const LaunchCtx& lc, const float* x, const float* y, float* out, int64_t A, int64_t R, int K, int N) {
+    const int KT = K < kGsrThreads ? K : kGsrThreads;
+    k_gsr_fwd<<<(unsigned)R, kGsrThreads, sizeof(float) * (size_t)(kGsrThreads / KT) * K, lc.stream>>>(x, y, out, A, R, K, N);
+    count(lc);
+}
+void gsr_vjp(const LaunchCtx& lc, const float* x, const float* y, const float* ct, float* dx, float* dy, int64_t A, int64_t R, int K, int N) {
+    const size_t smem = gsr_vjp_smem(K, N);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_gsr_vjp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_gsr_vjp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_done = true;
+    }
+    // rows per CTA: one, until there are more rows than 4 waves of CTAs (measured at R = 64: 4 rows per CTA is 1.8x SLOWER — the rows
+    // of one CTA are serialised latency chains, and the K*N reds per CTA were never the bottleneck)
+    int RB = (int)((R + 4 * (int64_t)lc.num_sms - 1) / (4 * (int64_t)lc.num_sms));
+    if (RB < 1) RB = 1;
+    const unsigned grid = (unsigned)((R + RB - 1) / RB);
+    if ((int64_t)K * N <= 8 * kGsrThreads) k_gsr_vjp<8><<<grid, kGsrThreads, smem, lc.stream>>>(x, y, ct, dx, dy, A, R, K, N, RB);
+    else k_gsr_vjp<0><<<grid, kGsrThreads, smem, lc.stream>>>(x, y, ct, dx, dy, A, R, K, N, RB);
     count(lc);
 }
 

@@ -74,6 +74,11 @@ void broadcast_rows(const LaunchCtx&, const float* row, float* out, int64_t n, i
 void diag_embed(const LaunchCtx&, const float* v, float* out, int64_t n, int rank);
 void diag_extract(const LaunchCtx&, const float* a, float* out, int64_t n, int rank);
 
+// ---- `gmul lM 1 lN >>> sumRows` fused (x viewed as [A, R, K], y as [K, N]): out[R,N]; VJP writes dx[A,R,K] and reds into the PRE-ZEROED dy[K,N]
+bool gsr_fits(int64_t K, int64_t N);
+void gsr_fwd(const LaunchCtx&, const float* x, const float* y, float* out, int64_t A, int64_t R, int K, int N);
+void gsr_vjp(const LaunchCtx&, const float* x, const float* y, const float* ct, float* dx, float* dy, int64_t A, int64_t R, int K, int N);
+
 // ---- losses / softmax (rows = samples)
 void softmax_rows(const LaunchCtx&, const float* Z, float* A, int64_t rows, int64_t cols);   // exp / sum exp, no max-subtraction (NeuralNet.hs:52-59)
 // dZ = VJP of the reference softmax TOp given dA (A not needed: recomputed from Z like the reference's closures)

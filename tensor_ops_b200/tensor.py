@@ -271,6 +271,17 @@ class CuTensor:
         return x._new(L.lib.tops_gmul, lM, lO, lN, x.b, y.b)
 
     @staticmethod
+    def gmulSumRows(lM: int, lO: int, lN: int, x: "CuTensor", y: "CuTensor") -> "CuTensor":
+        """`gmul lM lO lN >>> sumRows` fused (tops_gmul_sum_rows): one pass over x, no [A, ...] intermediate."""
+        return x._new(L.lib.tops_gmul_sum_rows, lM, lO, lN, x.b, y.b)
+
+    @staticmethod
+    def gmulSumRowsVJP(lM: int, lO: int, lN: int, x: "CuTensor", y: "CuTensor", ct: "CuTensor"):
+        dx, dy = L.c_buf(), L.c_buf()
+        x.ctx.check(L.lib.tops_gmul_sum_rows_vjp(x.ctx.h, lM, lO, lN, x.b, y.b, ct.b, C.byref(dx), C.byref(dy)))
+        return CuTensor(x.ctx, dx), CuTensor(x.ctx, dy)
+
+    @staticmethod
     def sumT(xs: Sequence["CuTensor"]) -> "CuTensor":
         """`sumT` (Types.hs:69)."""
         if len(xs) == 1:

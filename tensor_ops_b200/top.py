@@ -101,9 +101,32 @@ def compose(o2: TOp, o1: TOp) -> TOp:
     here that forward is taken from the saved activations of the enclosing gradient evaluation when it has already run
     (see `saved_activations`), so a chain of n ops costs O(n) launches instead of O(n^2)."""
     assert o1.n_out == o2.n_in, f"cannot compose: {o1.n_out} outputs into {o2.n_in} inputs"
+    fused = _fuse(o2, o1)
+    if fused is not None:
+        return fused
     return TOp(lambda T, xs: o2.run(T, _run_saved(o1, T, xs)),
                lambda T, xs, ds: o1.grad_(T, xs, o2.grad_(T, _run_saved(o1, T, xs), ds)),
                o1.n_in, o2.n_out, ("seq", o1.tag, o2.tag))
+
+
+def _fuse(o2: TOp, o1: TOp) -> Optional[TOp]:
+    """Rewrites applied when two primitives are composed (the deferred evaluator's fusion rules; tags describe structure).
+    gmul lM lO lN >>> sumRows, lM >= 1: the row sum commutes with the contraction — a backend that offers `gmulSumRows` evaluates
+    the pair (and its VJP) as one primitive; any other backend evaluates the plain composition."""
+    if o1.tag[:1] == ("gmul",) and o2.tag == ("sumRows",) and o1.tag[1] >= 1:
+        _, lM, lO, lN = o1.tag
+
+        def run(T, xs):
+            if hasattr(T, "gmulSumRows"):
+                return [T.gmulSumRows(lM, lO, lN, xs[0], xs[1])]
+            return o2.run(T, _run_saved(o1, T, xs))
+
+        def grad(T, xs, ds):
+            if hasattr(T, "gmulSumRowsVJP"):
+                return list(T.gmulSumRowsVJP(lM, lO, lN, xs[0], xs[1], ds[0]))
+            return o1.grad_(T, xs, o2.grad_(T, _run_saved(o1, T, xs), ds))
+        return TOp(run, grad, 2, 1, ("gmul_sumRows", lM, lO, lN))
+    return None
 
 
 def idOp(n: int) -> TOp:

@@ -32,7 +32,7 @@ def test_recorded_rank3_contraction_replays_on_new_inputs(ctx):
     with ctx.record() as g:
         (out,) = TO.runTOp(op, [x, y])
         dx, dy = TO.gradTOp_(op, [x, y], [d])
-    assert g.kernel_count() >= 3
+    assert 1 <= g.kernel_count() <= 3          # forward fused to one kernel, VJP to one (tops_gmul_sum_rows*)
     for trial in range(3):
         if trial:   # new values in the SAME input tensors, no re-recording
             hx, hy, hd = (rng.normal(size=s).astype(np.float32) for s in ((64, 64, 64), (64, 64), (64, 64)))
