@@ -13,6 +13,9 @@
 -- apps select hmatrix today (@Proxy \@(BTensorV CuMat)@ instead of @Proxy \@(BTensorV (HMat Double))@,
 -- app/Dots.hs:145).  `Tensor (BTensor v CuMat)` then comes for free from Backend/BTensor.hs:775-786.
 --
+-- The flat-storage `instance Tensor CuTensor` (rank >= 3 without nested boxed vectors, rank-0 results kept on the device) is the
+-- sibling module TensorOps.Backend.Cuda; this one is the `BLAS` dictionary for users who want to keep `BTensor`.
+--
 -- STATUS: written against include/tops_b200.h; NOT COMPILED — there is no GHC in the build image (SURVEY.md fact 5).
 -- It is deliberately thin and mechanical: every method is one foreign call; all arithmetic, shape checks and error
 -- reporting live behind the C ABI, which is what tests/ exercises.
@@ -29,6 +32,8 @@ module TensorOps.BLAS.Cuda
   ( CuMat
   , Sc(..)
   , withCuda
+  -- * shared with TensorOps.Backend.Cuda (`instance Tensor CuTensor`)
+  , Ctx, Buf, Dev(..), theCtx, check, newOut, pureOut, withDev, scalarOf, compile, shapeOf, download, unLit
   ) where
 
 import           Data.IORef
@@ -158,6 +163,49 @@ instance Floating Sc where
 
 unsup :: String -> a
 unsup f = error ("TensorOps.BLAS.Cuda: " ++ f ++ " has no TOPS_OP_* opcode yet")
+
+-- The reference asks for MORE than `Floating`: `instance Tensor (BTensor v b)` needs `RealFloat (ElemB b)` (BTensor.hs:775-785),
+-- `TOp`'s fields are `forall t. (Tensor t, RealFloat (ElemT t)) => ...` (Types.hs:122-125) and `VFunc` closures are
+-- `forall a. RealFloat a` (Types.hs:114-117).  `RealFloat` drags in Eq / Ord / Real / RealFrac, which a symbolic expression can
+-- only answer for literals: every method below is total on `Lit` and an `error` on a symbolic argument — a closure that BRANCHES
+-- on its tensor argument (compares, rounds, decodes it) cannot be reified into one elementwise program and is reported as such.
+-- None of the reference's own TOps do (logistic, softmax, the losses, `ad`'s `diff`/`grad` use only Num/Fractional/Floating).
+symbolic :: String -> a
+symbolic f = error ("TensorOps.BLAS.Cuda: " ++ f ++ " on a symbolic element — the lifted closure inspects its argument instead of computing with it")
+
+instance Eq Sc where
+    Lit a == Lit b = a == b
+    _     == _     = symbolic "(==)"
+instance Ord Sc where
+    compare (Lit a) (Lit b) = compare a b
+    compare _       _       = symbolic "compare"
+    -- `max` / `min` do have opcodes (TOPS_OP_MAX = 14, TOPS_OP_MIN = 15): a ReLU-style `max 0 x` stays liftable
+    max (Lit a) (Lit b) = Lit (max a b); max a b = Bin 14 a b
+    min (Lit a) (Lit b) = Lit (min a b); min a b = Bin 15 a b
+instance Real Sc where
+    toRational (Lit a) = toRational a
+    toRational _       = symbolic "toRational"
+instance RealFrac Sc where
+    properFraction (Lit a) = let (n, f) = properFraction a in (n, Lit f)
+    properFraction _       = symbolic "properFraction"
+instance RealFloat Sc where
+    floatRadix     _ = floatRadix     (0 :: Float)
+    floatDigits    _ = floatDigits    (0 :: Float)
+    floatRange     _ = floatRange     (0 :: Float)
+    decodeFloat (Lit a) = decodeFloat a
+    decodeFloat _       = symbolic "decodeFloat"
+    encodeFloat m e     = Lit (encodeFloat m e)
+    isNaN          = litOnly "isNaN" isNaN
+    isInfinite     = litOnly "isInfinite" isInfinite
+    isDenormalized = litOnly "isDenormalized" isDenormalized
+    isNegativeZero = litOnly "isNegativeZero" isNegativeZero
+    isIEEE         _ = True
+    atan2 (Lit a) (Lit b) = Lit (atan2 a b)
+    atan2 _       _       = unsup "atan2"
+
+litOnly :: String -> (Float -> Bool) -> Sc -> Bool
+litOnly _ f (Lit a) = f a
+litOnly n _ _       = symbolic n
 
 -- | postfix program + constant pool for `tops_lift`
 compile :: Sc -> ([Int32], [Float])

@@ -128,10 +128,12 @@ int tops_sum(tops_ctx*, const tops_buf* x, tops_buf** out_scalar);              
 /* liftB / liftT (BLAS.hs:92-96, Types.hs:56-59): n-ary elementwise map.  The reference passes a host closure
  * `Vec n a -> a`; a device cannot call it per element, so the closure is reified by applying it to symbolic
  * variables on the host side and shipping the expression as postfix bytecode (see TOPS_OP_* below).
- * Known programs (logistic, d*logistic'(x), exp, recip, log, p - r*g, ...) are matched to fused kernels; anything
- * else runs in a per-thread stack interpreter — still on the device, never on the host. */
+ * A catalogue of exact programs — every single unary / binary opcode, 1/x, d*logistic'(x) as `map'` builds it, p - r*g, (a-b)^2:
+ * the closures the reference's own TOps lift — is served by specialised float4 kernels (HBM-bound); anything else runs in a
+ * per-thread stack interpreter — still on the device, never on the host.  tops_lift_catalogue_hits() counts the former. */
 int tops_lift(tops_ctx*, const int32_t* prog, int prog_len, const float* consts, int n_consts,
               int n_in, const tops_buf* const* in, int rank, const int64_t* dims, tops_buf** out);
+int64_t tops_lift_catalogue_hits(void);
 
 enum {
     TOPS_OP_VAR = 0,    /* arg: input index      push in[arg][i]      */

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "tops_get_diag": (C.c_int, [c_ctx, c_buf, c_bufp]),
     "tops_sum": (C.c_int, [c_ctx, c_buf, c_bufp]),
     "tops_lift": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, c_bufp, C.c_int, c_i64p, c_bufp]),
+    "tops_lift_catalogue_hits": (C.c_int64, []),
     "tops_gmul": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, c_buf, c_buf, c_bufp]),
     "tops_gmul_sum_rows": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, c_buf, c_buf, c_bufp]),
     "tops_gmul_sum_rows_vjp": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, c_buf, c_buf, c_buf, c_bufp, c_bufp]),

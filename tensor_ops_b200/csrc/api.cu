@@ -459,6 +459,7 @@ extern "C" int tops_profile_summary(tops_ctx* ctx, char* out, size_t cap) {
     return TOPS_OK;
 }
 extern "C" int64_t tops_launch_count(tops_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int64_t tops_lift_catalogue_hits(void) { return k::g_lift_catalogue_hits; }
 extern "C" int tops_device_sm_count(tops_ctx* ctx) { return ctx ? ctx->num_sms : -1; }
 
 // ================================================================================================ storage

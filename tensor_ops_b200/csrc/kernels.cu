@@ -6,6 +6,8 @@
 
 #include <cuda_bf16.h>
 
+#include <initializer_list>
+
 #include "gemm_sm100.cuh"   // epilogue enums, act_apply / act_deriv_from_out
 
 namespace tops {
@@ -692,8 +694,77 @@ void bias_act(const LaunchCtx& lc, int act, const float* Z, const float* bias, f
     k_bias_act<<<grid_for(lc, rows * cols), kThreads, 0, lc.stream>>>(act, Z, bias, A, rows, cols);
     count(lc);
 }
+// Catalogue of lifted programs that get a specialised float4 kernel instead of the stack interpreter (HBM-bound instead of
+// ALU-bound): exactly the closures the reference's own TOps lift (NeuralNet.hs:38-50 logistic / d * logistic'(x) as `map'` builds
+// it, exp / log / recip of softmax and crossEntropy NeuralNet.hs:52-77, the SGD rule p - r*g FeedForward.hs:141-147, the squared
+// difference of squaredError) plus every single unary / binary opcode.  Matching is exact on the bytecode.
+namespace {
+constexpr int32_t ins(int op, int arg = 0) { return (op << 16) | arg; }
+bool prog_is(const LiftProgram& p, std::initializer_list<int32_t> code) {
+    if (p.len != (int)code.size()) return false;
+    int i = 0;
+    for (int32_t c : code) if (p.code[i++] != c) return false;
+    return true;
+}
+template <typename F> void launch_map1(const LaunchCtx& lc, const float* x, float* out, int64_t n, F f) {
+    k_map1<<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(x, out, n, aligned16(x) && aligned16(out), f); count(lc);
+}
+template <typename F> void launch_map2(const LaunchCtx& lc, const float* x, const float* y, float* out, int64_t n, F f) {
+    k_map2<<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(x, y, out, n, aligned16(x) && aligned16(y) && aligned16(out), f); count(lc);
+}
+bool lift_catalogue(const LaunchCtx& lc, const LiftProgram& p, int n_in, const float* const* in, float* out, int64_t n) {
+    if (p.len == 2 && (p.code[0] >> 16) == 0 && (p.code[0] & 0xffff) < n_in) {          // [VAR a, unary]
+        const float* x = in[p.code[0] & 0xffff];
+        switch (p.code[1] >> 16) {
+            case 6: launch_map1(lc, x, out, n, [] __device__(float a) { return -a; }); return true;
+            case 7: launch_map1(lc, x, out, n, [] __device__(float a) { return __expf(a); }); return true;
+            case 8: launch_map1(lc, x, out, n, [] __device__(float a) { return __logf(a); }); return true;
+            case 9: launch_map1(lc, x, out, n, [] __device__(float a) { return __fdividef(1.0f, a); }); return true;
+            case 10: launch_map1(lc, x, out, n, [] __device__(float a) { return sqrtf(a); }); return true;
+            case 11: launch_map1(lc, x, out, n, [] __device__(float a) { return tanhf(a); }); return true;
+            case 12: launch_map1(lc, x, out, n, [] __device__(float a) { return fabsf(a); }); return true;
+            case 17: launch_map1(lc, x, out, n, [] __device__(float a) { return __fdividef(1.0f, 1.0f + __expf(-a)); }); return true;
+            default: return false;
+        }
+    }
+    if (n_in >= 1 && prog_is(p, {ins(1, 0), ins(0, 0), ins(5)}) && p.consts[0] == 1.0f) {  // 1 / x
+        launch_map1(lc, in[0], out, n, [] __device__(float a) { return __fdividef(1.0f, a); }); return true;
+    }
+    if (n_in < 2) return false;
+    if (p.len == 3 && (p.code[0] >> 16) == 0 && (p.code[1] >> 16) == 0 && (p.code[0] & 0xffff) < n_in && (p.code[1] & 0xffff) < n_in) {   // [VAR a, VAR b, binary]
+        const float *x = in[p.code[0] & 0xffff], *y = in[p.code[1] & 0xffff];
+        switch (p.code[2] >> 16) {
+            case 2: launch_map2(lc, x, y, out, n, [] __device__(float a, float b) { return a + b; }); return true;
+            case 3: launch_map2(lc, x, y, out, n, [] __device__(float a, float b) { return a - b; }); return true;
+            case 4: launch_map2(lc, x, y, out, n, [] __device__(float a, float b) { return a * b; }); return true;
+            case 5: launch_map2(lc, x, y, out, n, [] __device__(float a, float b) { return a / b; }); return true;
+            case 14: launch_map2(lc, x, y, out, n, [] __device__(float a, float b) { return fmaxf(a, b); }); return true;
+            case 15: launch_map2(lc, x, y, out, n, [] __device__(float a, float b) { return fminf(a, b); }); return true;
+            default: return false;
+        }
+    }
+    if (prog_is(p, {ins(0, 0), ins(1, 0), ins(0, 1), ins(4), ins(3)})) {                  // p - r * g          (trainNetwork's zip)
+        const float r = p.consts[0];
+        launch_map2(lc, in[0], in[1], out, n, [r] __device__(float a, float g) { return a - r * g; }); return true;
+    }
+    if (prog_is(p, {ins(0, 0), ins(0, 1), ins(17), ins(1, 0), ins(0, 1), ins(17), ins(3), ins(4), ins(4)}) && p.consts[0] == 1.0f) {
+        launch_map2(lc, in[0], in[1], out, n, [] __device__(float d, float x) {                // d * logistic'(x)   (map' logistic logistic')
+            const float s = __fdividef(1.0f, 1.0f + __expf(-x));
+            return d * (s * (1.0f - s));
+        });
+        return true;
+    }
+    if (prog_is(p, {ins(0, 0), ins(0, 1), ins(3), ins(0, 0), ins(0, 1), ins(3), ins(4)})) { // (a - b)^2          (squaredError's zip)
+        launch_map2(lc, in[0], in[1], out, n, [] __device__(float a, float b) { const float d = a - b; return d * d; }); return true;
+    }
+    return false;
+}
+}  // namespace
+
+int64_t g_lift_catalogue_hits = 0;   // instrumentation (tests): programs served by a specialised kernel
 void lift(const LaunchCtx& lc, const LiftProgram& prog, int n_in, const float* const* in, float* out, int64_t n) {
     if (n <= 0) return;
+    if (lift_catalogue(lc, prog, n_in, in, out, n)) { ++g_lift_catalogue_hits; return; }
     InPtrs ip{};
     bool vec = aligned16(out);
     for (int j = 0; j < n_in; ++j) { ip.p[j] = in[j]; vec = vec && aligned16(in[j]); }

@@ -52,6 +52,7 @@ void bias_act(const LaunchCtx&, int act, const float* Z, const float* bias, floa
 // lift: postfix program, up to 8 inputs
 struct LiftProgram { int len; int n_consts; int32_t code[64]; float consts[16]; };
 void lift(const LaunchCtx&, const LiftProgram& prog, int n_in, const float* const* in, float* out, int64_t n);
+extern int64_t g_lift_catalogue_hits;   // programs served by a specialised kernel instead of the interpreter (process-wide counter)
 
 // out_mc[i] (+)= src[i] in EVERY replica bound to the NVLS multicast address out_mc (multimem.red); n fp32 elements
 void mc_push(const LaunchCtx&, const float* src, float* out_mc, int64_t n);

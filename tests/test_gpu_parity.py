@@ -324,6 +324,15 @@ def test_lift_catalogue_and_interpreter(ctx):
     rng = np.random.default_rng(12)
     x = rng.normal(size=(33, 17)); y = rng.uniform(0.5, 2.0, size=(33, 17)); dx, dy = ctx.from_numpy(x), ctx.from_numpy(y)
     T = tb.CuTensor
+    hits = tb._lib.lib.tops_lift_catalogue_hits
+    h0 = hits()
+    T.liftT(E.logistic, [dx]); T.liftT(lambda d, v: d * E.logistic_(v), [dy, dx]); T.liftT(E.exp, [dx]); T.liftT(E.log, [dy]); T.liftT(E.recip, [dy])
+    T.liftT(lambda p, g: p - 0.02 * g, [dx, dy]); T.liftT(lambda a, b: (a - b) * (a - b), [dx, dy]); T.liftT(lambda a, b: a * b, [dx, dy])
+    assert hits() - h0 == 8, "the reference's own lifted closures are all served by specialised kernels"
+    T.liftT(lambda a, b: E.tanh(a) ** 2 + E.sqrt(b * b + 1) / (1 + a * a), [dx, dy])
+    assert hits() - h0 == 8, "a program outside the catalogue runs in the interpreter"
+    close(T.liftT(lambda a, b: (a - b) * (a - b), [dx, dy]), (x - y) ** 2, 1e-6, "(a-b)^2")
+    close(T.liftT(lambda a, b: a * b, [dx, dy]), x * y, 1e-6, "a*b")
     close(T.liftT(E.logistic, [dx]), 1 / (1 + np.exp(-x)), 1e-6, "logistic")
     close(T.liftT(lambda d, v: d * E.logistic_(v), [dy, dx]), y * (lambda s: s * (1 - s))(1 / (1 + np.exp(-x))), 1e-6, "d*logistic'")
     close(T.liftT(E.exp, [dx]), np.exp(x), 1e-6, "exp"); close(T.liftT(E.log, [dy]), np.log(y), 1e-5, "log")
