@@ -26,6 +26,15 @@ inline int grid_for(const LaunchCtx& lc, int64_t work_items, int per_block = kTh
 }
 inline void count(const LaunchCtx& lc) { if (lc.launches) ++*lc.launches; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// 2-D grid for row/column kernels: x covers `col_items` work items (kThreads per block), y walks the rows with ~8 waves of CTAs in total
+inline dim3 grid_rows_cols(const LaunchCtx& lc, int64_t rows, int64_t col_items) {
+    const int64_t gx = (col_items + kThreads - 1) / kThreads;
+    int64_t gy = ((int64_t)lc.num_sms * 8 + gx - 1) / gx;
+    if (gy > rows) gy = rows;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    return dim3((unsigned)gx, (unsigned)gy);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -59,8 +68,13 @@ __device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f); }
 
-__global__ void k_fill(float* p, int64_t n, float v) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+// 16-byte stores when the base is 16-byte aligned, scalar tail
+__global__ void k_fill(float* p, int64_t n, float v, bool vec) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = vec ? n / 4 : 0;
+    const float4 v4 = make_float4(v, v, v, v);
+    for (int64_t i = tid; i < n4; i += nth) reinterpret_cast<float4*>(p)[i] = v4;
+    for (int64_t i = n4 * 4 + tid; i < n; i += nth) p[i] = v;
 }
 __global__ void k_fill_bf16(__nv_bfloat16* p, int64_t n, float v) {
     const __nv_bfloat16 b = __float2bfloat16_rn(v);
@@ -85,11 +99,31 @@ __global__ void k_rand(float* p, int64_t n, float a, float b, uint64_t seed) {
         for (int e = 0; e < 4; ++e) if (i * 4 + e < n) p[i * 4 + e] = v[e];
     }
 }
-__global__ void k_cast_f2b(const float* s, __nv_bfloat16* d, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = __float2bfloat16_rn(s[i]);
+// 8 elements per thread: 2 x 16-byte fp32 accesses against one 16-byte bf16 access
+__global__ void k_cast_f2b(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, int64_t n, bool vec) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n8 = vec ? n / 8 : 0;
+    for (int64_t i = tid; i < n8; i += nth) {
+        const float4 a = reinterpret_cast<const float4*>(s)[2 * i], b = reinterpret_cast<const float4*>(s)[2 * i + 1];
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+        h[0] = __floats2bfloat162_rn(a.x, a.y); h[1] = __floats2bfloat162_rn(a.z, a.w);
+        h[2] = __floats2bfloat162_rn(b.x, b.y); h[3] = __floats2bfloat162_rn(b.z, b.w);
+        reinterpret_cast<uint4*>(d)[i] = u;
+    }
+    for (int64_t i = n8 * 8 + tid; i < n; i += nth) d[i] = __float2bfloat16_rn(s[i]);
 }
-__global__ void k_cast_b2f(const __nv_bfloat16* s, float* d, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = __bfloat162float(s[i]);
+__global__ void k_cast_b2f(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, int64_t n, bool vec) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n8 = vec ? n / 8 : 0;
+    for (int64_t i = tid; i < n8; i += nth) {
+        const uint4 u = reinterpret_cast<const uint4*>(s)[i];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+        const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+        reinterpret_cast<float4*>(d)[2 * i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        reinterpret_cast<float4*>(d)[2 * i + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+    }
+    for (int64_t i = n8 * 8 + tid; i < n; i += nth) d[i] = __bfloat162float(s[i]);
 }
 __global__ void k_eye(float* p, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (i / n == i % n) ? 1.f : 0.f;
@@ -137,10 +171,24 @@ __global__ void k_add_n(InPtrs in, int n_in, float* __restrict__ out, int64_t n,
     }
 }
 
+// [rows, cols] row-major, no div/mod per element: blockIdx.x / threadIdx.x walk 4-column chunks (the thread's bias chunk stays in
+// registers), blockIdx.y walks rows.  VEC: cols % 4 == 0 and 16-byte aligned bases.
+template <bool VEC>
 __global__ void k_bias_act(int act, const float* __restrict__ Z, const float* __restrict__ bias, float* __restrict__ A, int64_t rows, int64_t cols) {
-    const int64_t n = rows * cols;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        A[i] = act_apply(act, Z[i] + (bias ? bias[i % cols] : 0.f));
+    constexpr int W = VEC ? 4 : 1;
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * W;
+    if (c >= cols) return;
+    float b[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) b[e] = bias ? bias[c + e] : 0.f;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        if constexpr (VEC) {
+            const float4 z = *reinterpret_cast<const float4*>(Z + r * cols + c);
+            *reinterpret_cast<float4*>(A + r * cols + c) = make_float4(act_apply(act, z.x + b[0]), act_apply(act, z.y + b[1]), act_apply(act, z.z + b[2]), act_apply(act, z.w + b[3]));
+        } else {
+            A[r * cols + c] = act_apply(act, Z[r * cols + c] + b[0]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ liftT interpreter: 4 elements per thread
@@ -218,9 +266,28 @@ __global__ void k_lift(LiftProgram prog, InPtrs in, int n_in, float* __restrict_
 template <bool DOT>
 __global__ void k_reduce_partial(const float* __restrict__ x, const float* __restrict__ y, int64_t n, float* __restrict__ partial) {
     __shared__ float sh[32];
-    float acc = 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        acc += DOT ? x[i] * y[i] : x[i];
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!DOT || (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const int64_t n4 = vec ? n / 4 : 0;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains: 16-byte loads, two of them in flight per thread
+    int64_t i = tid;
+    for (; i + nth < n4; i += 2 * nth) {
+        const float4 u = reinterpret_cast<const float4*>(x)[i], v = reinterpret_cast<const float4*>(x)[i + nth];
+        if (DOT) {
+            const float4 p = reinterpret_cast<const float4*>(y)[i], q = reinterpret_cast<const float4*>(y)[i + nth];
+            a0 = fmaf(u.x, p.x, a0); a1 = fmaf(u.y, p.y, a1); a2 = fmaf(u.z, p.z, a2); a3 = fmaf(u.w, p.w, a3);
+            a0 = fmaf(v.x, q.x, a0); a1 = fmaf(v.y, q.y, a1); a2 = fmaf(v.z, q.z, a2); a3 = fmaf(v.w, q.w, a3);
+        } else {
+            a0 += u.x + v.x; a1 += u.y + v.y; a2 += u.z + v.z; a3 += u.w + v.w;
+        }
+    }
+    for (; i < n4; i += nth) {
+        const float4 u = reinterpret_cast<const float4*>(x)[i];
+        if (DOT) { const float4 p = reinterpret_cast<const float4*>(y)[i]; a0 = fmaf(u.x, p.x, a0); a1 = fmaf(u.y, p.y, a1); a2 = fmaf(u.z, p.z, a2); a3 = fmaf(u.w, p.w, a3); }
+        else { a0 += u.x; a1 += u.y; a2 += u.z; a3 += u.w; }
+    }
+    for (int64_t j = n4 * 4 + tid; j < n; j += nth) a0 += DOT ? x[j] * y[j] : x[j];
+    float acc = (a0 + a1) + (a2 + a3);
     acc = block_sum(acc, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
@@ -248,17 +315,29 @@ __global__ void k_colsum_partial(const TIn* __restrict__ x, const float* __restr
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
     const int64_t r1 = min(rows, r0 + rows_per_chunk);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t r = r0 + warp; r < r1; r += 8) {
-        const float wr = w ? w[r] : 1.0f;
-        const TIn* row = x + r * cols + c0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t c = c0 + lane + 32 * j;
-            if (c < cols) acc[j] = fmaf(wr, (float)row[lane + 32 * j], acc[j]);
+    // fp32 with 16-byte aligned rows: lane owns 4 CONSECUTIVE columns (one 16-byte load per row); otherwise columns lane + 32 j
+    const bool vec4 = sizeof(TIn) == 4 && (cols % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && c0 + 128 <= cols;
+    if (vec4) {
+        for (int64_t r = r0 + warp; r < r1; r += 8) {
+            const float wr = w ? w[r] : 1.0f;
+            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + r * cols + c0 + lane * 4);
+            acc[0] = fmaf(wr, v.x, acc[0]); acc[1] = fmaf(wr, v.y, acc[1]); acc[2] = fmaf(wr, v.z, acc[2]); acc[3] = fmaf(wr, v.w, acc[3]);
         }
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sh[warp][lane + 32 * j] = acc[j];
+        for (int j = 0; j < 4; ++j) sh[warp][lane * 4 + j] = acc[j];
+    } else {
+        for (int64_t r = r0 + warp; r < r1; r += 8) {
+            const float wr = w ? w[r] : 1.0f;
+            const TIn* row = x + r * cols + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t c = c0 + lane + 32 * j;
+                if (c < cols) acc[j] = fmaf(wr, (float)row[lane + 32 * j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh[warp][lane + 32 * j] = acc[j];
+    }
     __syncthreads();
     if (threadIdx.x < 128) {
         float s = 0.f;
@@ -277,9 +356,21 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int chunks, in
 }
 
 // ------------------------------------------------------------------ BLAS-2 / layout
-__global__ void k_ger(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t n, int64_t m) {
-    const int64_t tot = n * m;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) out[i] = x[i / m] * y[i % m];
+// out[r, c] = (x ? x[r] : 1) * y[c]: `ger` (x != NULL) and `broadcast_rows` (x == NULL).  Same 2-D scheme as k_bias_act: the
+// thread's 4 columns of y stay in registers, rows are walked by blockIdx.y — one 16-byte store per row and thread, no div/mod.
+template <bool VEC>
+__global__ void k_outer_rows(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out, int64_t n, int64_t m) {
+    constexpr int W = VEC ? 4 : 1;
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * W;
+    if (c >= m) return;
+    float v[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) v[e] = y[c + e];
+    for (int64_t r = blockIdx.y; r < n; r += gridDim.y) {
+        const float a = x ? x[r] : 1.0f;
+        if constexpr (VEC) *reinterpret_cast<float4*>(out + r * m + c) = make_float4(a * v[0], a * v[1], a * v[2], a * v[3]);
+        else out[r * m + c] = a * v[0];
+    }
 }
 // one warp per output row; A row-major [n,m]
 __global__ void k_gemv_rows(float alpha, const float* __restrict__ a, const float* __restrict__ x, float beta, const float* __restrict__ y, float* __restrict__ out, int64_t n, int64_t m, bool vec) {
@@ -325,9 +416,28 @@ __global__ void k_permute(const float* __restrict__ in, float* __restrict__ out,
         out[i] = in[off];
     }
 }
-__global__ void k_broadcast_rows(const float* __restrict__ row, float* __restrict__ out, int64_t n, int64_t m) {
-    const int64_t tot = n * m;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) out[i] = row[i % m];
+// Permutation whose output's fastest axis is NOT the input's fastest axis (e.g. `transp` of a rank-3 tensor = full reversal):
+// a 32 x 32 shared-memory tile over (p = the input's last axis, q = the axis that becomes the output's last) makes both the reads
+// and the writes coalesced; the remaining axes form a batch whose index is decomposed ONCE per block, not per element.
+struct PermTiled { int nb; int64_t bdim[8], bin[8], bout[8]; int64_t P, Q, p_out_stride, q_in_stride; };
+__global__ void k_permute_tiled(const float* __restrict__ in, float* __restrict__ out, PermTiled pa) {
+    __shared__ float t[32][33];
+    int64_t rem = blockIdx.z, ioff = 0, ooff = 0;
+    for (int a = pa.nb - 1; a >= 0; --a) {
+        const int64_t idx = rem % pa.bdim[a];
+        rem /= pa.bdim[a];
+        ioff += idx * pa.bin[a]; ooff += idx * pa.bout[a];
+    }
+    const int64_t p0 = (int64_t)blockIdx.x * 32, q0 = (int64_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {        // read: rows = q, contiguous along p
+        const int64_t q = q0 + j, pp = p0 + threadIdx.x;
+        if (q < pa.Q && pp < pa.P) t[j][threadIdx.x] = in[ioff + q * pa.q_in_stride + pp];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {        // write: rows = p, contiguous along q
+        const int64_t pp = p0 + j, q = q0 + threadIdx.x;
+        if (q < pa.Q && pp < pa.P) out[ooff + pp * pa.p_out_stride + q] = t[threadIdx.x][j];
+    }
 }
 __global__ void k_diag_embed(const float* __restrict__ v, float* __restrict__ out, int64_t n, int64_t step) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i * step] = v[i];
@@ -649,12 +759,12 @@ void gsr_vjp(const LaunchCtx& lc, const float* x, const float* y, const float* c
     count(lc);
 }
 
-void fill(const LaunchCtx& lc, float* p, int64_t n, float v) { if (n <= 0) return; k_fill<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(p, n, v); count(lc); }
+void fill(const LaunchCtx& lc, float* p, int64_t n, float v) { if (n <= 0) return; k_fill<<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(p, n, v, aligned16(p)); count(lc); }
 void fill_bf16(const LaunchCtx& lc, void* p, int64_t n, float v) { if (n <= 0) return; k_fill_bf16<<<grid_for(lc, n), kThreads, 0, lc.stream>>>((__nv_bfloat16*)p, n, v); count(lc); }
 void rand_normal(const LaunchCtx& lc, float* p, int64_t n, float mean, float sd, uint64_t seed) { if (n <= 0) return; k_rand<true><<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(p, n, mean, sd, seed); count(lc); }
 void rand_uniform(const LaunchCtx& lc, float* p, int64_t n, float lo, float hi, uint64_t seed) { if (n <= 0) return; k_rand<false><<<grid_for(lc, (n + 3) / 4), kThreads, 0, lc.stream>>>(p, n, lo, hi, seed); count(lc); }
-void cast_f32_bf16(const LaunchCtx& lc, const float* s, void* d, int64_t n) { if (n <= 0) return; k_cast_f2b<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(s, (__nv_bfloat16*)d, n); count(lc); }
-void cast_bf16_f32(const LaunchCtx& lc, const void* s, float* d, int64_t n) { if (n <= 0) return; k_cast_b2f<<<grid_for(lc, n), kThreads, 0, lc.stream>>>((const __nv_bfloat16*)s, d, n); count(lc); }
+void cast_f32_bf16(const LaunchCtx& lc, const float* s, void* d, int64_t n) { if (n <= 0) return; k_cast_f2b<<<grid_for(lc, (n + 7) / 8), kThreads, 0, lc.stream>>>(s, (__nv_bfloat16*)d, n, aligned16(s) && aligned16(d)); count(lc); }
+void cast_bf16_f32(const LaunchCtx& lc, const void* s, float* d, int64_t n) { if (n <= 0) return; k_cast_b2f<<<grid_for(lc, (n + 7) / 8), kThreads, 0, lc.stream>>>((const __nv_bfloat16*)s, d, n, aligned16(s) && aligned16(d)); count(lc); }
 void eye(const LaunchCtx& lc, float* p, int64_t n) { if (n <= 0) return; k_eye<<<grid_for(lc, n * n), kThreads, 0, lc.stream>>>(p, n); count(lc); }
 
 void axpy(const LaunchCtx& lc, float alpha, const float* x, const float* y, float* out, int64_t n) {
@@ -691,7 +801,10 @@ void dact_mul(const LaunchCtx& lc, int act, const float* dA, const float* A, flo
 }
 void bias_act(const LaunchCtx& lc, int act, const float* Z, const float* bias, float* A, int64_t rows, int64_t cols) {
     if (rows * cols <= 0) return;
-    k_bias_act<<<grid_for(lc, rows * cols), kThreads, 0, lc.stream>>>(act, Z, bias, A, rows, cols);
+    const bool vec = (cols % 4) == 0 && aligned16(Z) && aligned16(A) && (!bias || aligned16(bias));
+    const dim3 g = grid_rows_cols(lc, rows, vec ? cols / 4 : cols);
+    if (vec) k_bias_act<true><<<g, kThreads, 0, lc.stream>>>(act, Z, bias, A, rows, cols);
+    else k_bias_act<false><<<g, kThreads, 0, lc.stream>>>(act, Z, bias, A, rows, cols);
     count(lc);
 }
 // Catalogue of lifted programs that get a specialised float4 kernel instead of the stack interpreter (HBM-bound instead of
@@ -773,12 +886,12 @@ void lift(const LaunchCtx& lc, const LiftProgram& prog, int n_in, const float* c
 }
 
 void sum_all(const LaunchCtx& lc, const float* x, int64_t n, float* out, float* ws) {
-    const int g = grid_for(lc, n > 0 ? n : 1, kThreads, 4);
+    const int g = grid_for(lc, n > 0 ? (n + 3) / 4 : 1, kThreads, 4);
     k_reduce_partial<false><<<g, kThreads, 0, lc.stream>>>(x, nullptr, n, ws); count(lc);
     k_reduce_final<<<1, kThreads, 0, lc.stream>>>(ws, g, out); count(lc);
 }
 void dot(const LaunchCtx& lc, const float* x, const float* y, int64_t n, float* out, float* ws) {
-    const int g = grid_for(lc, n > 0 ? n : 1, kThreads, 4);
+    const int g = grid_for(lc, n > 0 ? (n + 3) / 4 : 1, kThreads, 4);
     k_reduce_partial<true><<<g, kThreads, 0, lc.stream>>>(x, y, n, ws); count(lc);
     k_reduce_final<<<1, kThreads, 0, lc.stream>>>(ws, g, out); count(lc);
 }
@@ -811,7 +924,11 @@ void col_sums_bf16(const LaunchCtx& lc, const void* x, int64_t rows, int64_t col
 
 void ger(const LaunchCtx& lc, const float* x, const float* y, float* out, int64_t n, int64_t m) {
     if (n * m <= 0) return;
-    k_ger<<<grid_for(lc, n * m), kThreads, 0, lc.stream>>>(x, y, out, n, m); count(lc);
+    const bool vec = (m % 4) == 0 && aligned16(y) && aligned16(out);
+    const dim3 g = grid_rows_cols(lc, n, vec ? m / 4 : m);
+    if (vec) k_outer_rows<true><<<g, kThreads, 0, lc.stream>>>(x, y, out, n, m);
+    else k_outer_rows<false><<<g, kThreads, 0, lc.stream>>>(x, y, out, n, m);
+    count(lc);
 }
 void gemv(const LaunchCtx& lc, float alpha, const float* a, int a_tr, const float* x, float beta, const float* y, float* out, int64_t n, int64_t m) {
     if (n <= 0) return;
@@ -846,11 +963,37 @@ void permute(const LaunchCtx& lc, const float* in, float* out, int rank, const i
     const int64_t n = s;
     for (int a = 0; a < rank; ++a) { pa.out_dims[a] = in_dims[perm[a]]; pa.in_strides_for_out[a] = in_strides[perm[a]]; }
     if (n <= 0) return;
+    // output's fastest axis differs from the input's: tile over (input's last axis p, output's last axis q) through shared memory
+    if (rank >= 2 && perm[rank - 1] != rank - 1) {
+        PermTiled pt{};
+        int64_t out_strides[8];
+        int64_t so = 1;
+        for (int a = rank - 1; a >= 0; --a) { out_strides[a] = so; so *= pa.out_dims[a]; }
+        int p_out_axis = -1;                                   // where the input's last axis lands in the output
+        for (int a = 0; a < rank; ++a) if (perm[a] == rank - 1) p_out_axis = a;
+        pt.P = in_dims[rank - 1]; pt.Q = pa.out_dims[rank - 1];
+        pt.p_out_stride = out_strides[p_out_axis]; pt.q_in_stride = pa.in_strides_for_out[rank - 1];
+        int64_t batch = 1;
+        for (int a = 0; a < rank - 1; ++a) {                   // every output axis except q and p's landing place
+            if (a == p_out_axis) continue;
+            pt.bdim[pt.nb] = pa.out_dims[a]; pt.bin[pt.nb] = pa.in_strides_for_out[a]; pt.bout[pt.nb] = out_strides[a]; ++pt.nb;
+            batch *= pa.out_dims[a];
+        }
+        const int64_t gx = (pt.P + 31) / 32, gy = (pt.Q + 31) / 32;
+        if (gy <= 65535 && batch <= 65535) {
+            k_permute_tiled<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)batch), dim3(32, 8), 0, lc.stream>>>(in, out, pt); count(lc);
+            return;
+        }
+    }
     k_permute<<<grid_for(lc, n), kThreads, 0, lc.stream>>>(in, out, pa, n); count(lc);
 }
 void broadcast_rows(const LaunchCtx& lc, const float* row, float* out, int64_t n, int64_t m) {
     if (n * m <= 0) return;
-    k_broadcast_rows<<<grid_for(lc, n * m), kThreads, 0, lc.stream>>>(row, out, n, m); count(lc);
+    const bool vec = (m % 4) == 0 && aligned16(row) && aligned16(out);
+    const dim3 g = grid_rows_cols(lc, n, vec ? m / 4 : m);
+    if (vec) k_outer_rows<true><<<g, kThreads, 0, lc.stream>>>(nullptr, row, out, n, m);
+    else k_outer_rows<false><<<g, kThreads, 0, lc.stream>>>(nullptr, row, out, n, m);
+    count(lc);
 }
 static int64_t diag_step(int64_t n, int rank) { int64_t step = 0, s = 1; for (int a = 0; a < rank; ++a) { step += s; s *= n; } return step; }
 void diag_embed(const LaunchCtx& lc, const float* v, float* out, int64_t n, int rank) {
