@@ -1009,6 +1009,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ew.out1_s = p.out1_scale_ptr != nullptr ? __ldg(p.out1_scale_ptr) : 1.0f;
                 if (p.out1_row_scale != nullptr && row < p.M) ew.out1_s *= __ldg(p.out1_row_scale + row);
             }
+            bool lean_store = false;
+            // (instantiated for the dX layout only — A K-major, B MN-major: in the variant that carries the specialised forward epilogue
+            //  the extra code path costs registers — measured: 48 more bytes of spill and 8 % of the forward GEMM)
+            if constexpr (kPresplit && MA == MAJOR_K && MB == MAJOR_MN) {   // plain store of an interior tile (dX, gmul): stage + coalesced store, nothing else
+                lean_store = tma && p.epi == EPI_STORE && p.aux0 == nullptr && p.alpha == 1.0f && p.colsum == nullptr &&
+                             row0 + 32 <= p.M && n0 + half * HC + HC <= p.N && !(p.debug & 1);
+                if (lean_store) {
+#pragma unroll
+                    for (int c = 0; c < HC / 16; ++c) {            // the two staging blocks alternate: one __syncwarp per sub-block
+                        const uint32_t buf = (c & 1) ? ew.out_buf : ew.aux_buf;
+                        stage_write_row<float, 16>(buf, lane, *reinterpret_cast<float (*)[16]>(&sum[c * 16]));
+                        __syncwarp();
+                        stage_store_interior<float, 16>(buf, lane, p.out0, p.ld_out0, row0, n0 + half * HC + c * 16);
+                    }
+                    __syncwarp();
+                }
+            }
             if constexpr (kPresplit) {
                 if (lean) {
 #pragma unroll 1
@@ -1021,7 +1038,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
-            if (row0 < p.M && !lean) {
+            if (row0 < p.M && !lean && !lean_store) {
                 // ONE copy of the block code (the fused epilogue is large; unrolled four times it thrashes the instruction
                 // cache): always process sum[0..31], then rotate the register accumulators down by one block.
 #pragma unroll 1

@@ -1,4 +1,3 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 > gpurun_out/pytest_par.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_par.log
-tail -5 gpurun_out/pytest_par.log
-timeout 900 python tools/bench_bandwidth.py > gpurun_out/bench_bandwidth.log 2>&1; cat gpurun_out/bench_bandwidth.log | tail -25
+for i in 1 2; do
+timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-side --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['per_kernel_ms'], d['parity']['ok'], d['clocks'])"
+done
