@@ -8,6 +8,7 @@ KEYS = [
     ("dram__bytes_read.sum", "dram read"),
     ("dram__bytes_write.sum", "dram write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
+    ("dram__bytes.sum.per_second", "dram bytes per second"),
     ("lts__t_bytes.sum", "L2 bytes"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (elapsed)"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active % (active)"),
