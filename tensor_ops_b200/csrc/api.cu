@@ -37,6 +37,10 @@ struct tops_ctx {
     struct SplitScope* split_scope = nullptr;   // fp16 pairs already made inside the current API call
     struct tops_graph* capturing = nullptr;     // non-NULL between tops_graph_begin and tops_graph_end: allocations come from its arena
     int64_t launches = 0;
+    // lifetime: one reference for the handle returned by tops_init + one per live tops_buf; the struct is deleted by whoever drops the
+    // last one, so a buffer finalizer that runs after tops_shutdown (a host GC) still finds its context
+    std::atomic<int> refs{1};
+    bool shut = false;
     unsigned int* wd_host = nullptr;
     unsigned int* wd_dev = nullptr;
     float* scratch = nullptr;   // small persistent workspace for reductions (1 MiB)
@@ -86,7 +90,13 @@ int set_err(tops_ctx* ctx, int code, const char* fmt, ...) {
 }
 
 // serialise calls on the context and make its device current (a process may hold contexts on several devices)
-#define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu); cudaSetDevice((ctx)->device)
+// ... and restore the caller's device afterwards (GC finalizers of a host runtime call in here from arbitrary threads)
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu); DeviceGuard dev_guard_((ctx)->device)
 #define CHECK_CTX(ctx) do { if (!(ctx)) return TOPS_ERR_INVALID; } while (0)
 #define CUDA_TRY(ctx, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return set_err(ctx, TOPS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
 #define TRY(expr) do { int r_ = (expr); if (r_ != TOPS_OK) return r_; } while (0)
@@ -128,6 +138,7 @@ int new_buf(tops_ctx* ctx, int dtype, int rank, const int64_t* dims, void* data,
     }
     b->data = data; b->owns = owns; b->tr = false; b->parent = parent;
     if (parent) parent->refs.fetch_add(1);
+    ctx->refs.fetch_add(1);
     *out = b;
     return TOPS_OK;
 }
@@ -174,8 +185,10 @@ void release_buf(tops_buf* b) {
     while (b) {
         if (b->refs.fetch_sub(1) != 1) return;
         tops_buf* parent = b->parent;
-        if (b->owns && b->data) cudaFreeAsync(b->data, b->ctx->stream);
+        tops_ctx* ctx = b->ctx;
+        if (b->owns && b->data) { if (ctx->shut) cudaFree(b->data); else cudaFreeAsync(b->data, ctx->stream); }
         delete b;
+        if (ctx->refs.fetch_sub(1) == 1) delete ctx;      // only possible after tops_shutdown dropped the handle's reference
         b = parent;
     }
 }
@@ -394,7 +407,9 @@ extern "C" int tops_shutdown(tops_ctx* ctx) {
     if (ctx->wd_host) cudaFreeHost(ctx->wd_host);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    delete ctx;
+    ctx->scratch = nullptr; ctx->wd_host = nullptr; ctx->copy_stream = ctx->own_stream = ctx->stream = nullptr;
+    ctx->shut = true;                                      // buffers released from now on free synchronously and make no launches
+    if (ctx->refs.fetch_sub(1) == 1) delete ctx;
     return TOPS_OK;
 }
 
@@ -487,8 +502,13 @@ extern "C" int tops_buf_view(tops_ctx* ctx, tops_buf* parent, int64_t offset, in
 extern "C" int tops_buf_retain(tops_buf* b) { if (!b) return TOPS_ERR_INVALID; b->refs.fetch_add(1); return TOPS_OK; }
 extern "C" int tops_buf_release(tops_buf* b) {
     if (!b) return TOPS_ERR_INVALID;
-    tops_ctx* ctx = b->ctx; LOCK(ctx);
-    release_buf(b);
+    tops_ctx* ctx = b->ctx;
+    ctx->refs.fetch_add(1);                 // keep the context (and the mutex we hold) alive across a release that drops its last buffer
+    {
+        LOCK(ctx);
+        release_buf(b);
+    }
+    if (ctx->refs.fetch_sub(1) == 1) delete ctx;
     return TOPS_OK;
 }
 extern "C" int tops_buf_rank(const tops_buf* b) { return b ? b->rank : -1; }
@@ -1619,11 +1639,14 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
 extern "C" int tops_sgd_step(tops_ctx* ctx, int n, const tops_buf* const* params, const tops_buf* const* grads, double rate, tops_buf** out) {
     CHECK_CTX(ctx); LOCK(ctx);
     if (n < 0 || !params || !grads || !out) return set_err(ctx, TOPS_ERR_INVALID, "sgd_step: NULL argument");
+    Tmp tmp;
     for (int j = 0; j < n; ++j) {
         TRY(need_f32(ctx, params[j], "tops_sgd_step")); TRY(need_f32(ctx, grads[j], "tops_sgd_step"));
-        if (params[j]->tr || grads[j]->tr || !same_shape(params[j], grads[j])) return set_err(ctx, TOPS_ERR_SHAPE, "sgd_step: parameter %d and its gradient differ in shape", j);
-        TRY(prep_out(ctx, &out[j], TOPS_F32, params[j]->rank, params[j]->dims));
-        k::sgd(lc_of(ctx), (const float*)params[j]->data, (const float*)grads[j]->data, (float)rate, (float*)out[j]->data, params[j]->numel);
+        if (!same_shape(params[j], grads[j])) return set_err(ctx, TOPS_ERR_SHAPE, "sgd_step: parameter %d and its gradient differ in shape", j);
+        const tops_buf *ps, *gs;     // O(1) transposed views (e.g. a gradient that came through transpOp) are materialised
+        TRY(contig(ctx, params[j], tmp, &ps)); TRY(contig(ctx, grads[j], tmp, &gs));
+        TRY(prep_out(ctx, &out[j], TOPS_F32, ps->rank, ps->dims));
+        k::sgd(lc_of(ctx), (const float*)ps->data, (const float*)gs->data, (float)rate, (float*)out[j]->data, ps->numel);
     }
     return check_launch(ctx, "sgd_step");
 }

@@ -75,6 +75,8 @@ def _bin(op: str, a: Expr, b: Expr) -> Expr:
                  "max": max(x, y), "min": min(x, y), "pow": x ** y}[op]
         except (OverflowError, ValueError, ZeroDivisionError):
             v = None
+        if isinstance(v, complex) or (isinstance(v, float) and v != v):
+            v = None          # e.g. (-8.0) ** 0.5: Python answers with a complex; leave it to the device (NaN, like powf)
         if v is not None:
             return Expr.const(v)
     if op == "add":

@@ -91,10 +91,10 @@ class Context:
         p = C.c_void_p()
         self.check(L.lib.tops_host_alloc(C.c_size_t(4 * max(n, 1)), int(write_combined), C.byref(p)))
         buf = (C.c_float * max(n, 1)).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=np.float32, count=n).reshape(shape)
-        self._host_blocks = getattr(self, "_host_blocks", [])
-        self._host_blocks.append(_HostBlock(p.value, buf))      # freed when the context object goes away
-        return arr
+        # the ARRAY owns the block: arr.base -> memoryview -> buf -> _block, so the pinned memory lives exactly as long as any
+        # array (or view of it) does, independently of this Context object
+        buf._block = _HostBlock(p.value)
+        return np.frombuffer(buf, dtype=np.float32, count=n).reshape(shape)
 
     def wrap(self, device_ptr: int, dims, dtype: int = L.F32, keepalive=None) -> "CuTensor":
         """Non-owning view of caller-allocated device memory (e.g. a torch tensor's storage)."""
@@ -150,8 +150,8 @@ _default: Optional[Context] = None
 
 
 class _HostBlock:
-    def __init__(self, ptr, buf):
-        self.ptr, self.buf = ptr, buf
+    def __init__(self, ptr):
+        self.ptr = ptr
 
     def __del__(self):
         try:
