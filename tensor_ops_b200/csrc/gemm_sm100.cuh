@@ -90,7 +90,7 @@ struct GemmParams {
     const float* out1_scale_ptr;  // device scalar, NULL = 1
     const float* out1_row_scale;  // [M], NULL = 1
     unsigned int* watchdog;   // mapped host memory, 2 words
-    int debug;                // TOPS_GEMM_DEBUG bit mask (A/B experiments): 1 = no specialised forward epilogue
+    int debug;                // TOPS_GEMM_DEBUG bit mask (A/B experiments): 1 = no specialised forward epilogue, 2 = its one-sub-block-at-a-time variant
 };
 
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
@@ -596,6 +596,70 @@ __device__ __forceinline__ void epi_fwd_pair_lean(const GemmParams& p, const CUt
     __syncwarp();
 }
 
+// The same epilogue on a PAIR of sub-blocks (32 columns) at a time: both staging blocks of the warp serve both sub-blocks in every
+// phase (dA in, A out, dZ for the column sums, the fp16 pair out), so a 32-column step has 7 warp-synchronised phases instead of
+// 14 and every phase has twice the independent work in flight (the 8 epilogue warps are latency-bound: 2 per scheduler).
+// The two dA blocks of the NEXT pair are requested (one mbarrier, 4 KiB) when this pair's last staged bytes have been read, and
+// their latency hides behind the logistic of that pair, which does not need them.
+__device__ __forceinline__ void epi_issue_aux_pair(const CUtensorMap* tmAux, EpiWarp& w, int lane, int row0, int col) {
+    ptx::fence_proxy_async_smem();
+    if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(w.aux_bar, 2u * 32u * 16u * 4u);
+        ptx::tma_load_2d_s(w.aux_buf, tmAux, w.aux_bar, col, row0);
+        ptx::tma_load_2d_s(w.out_buf, tmAux, w.aux_bar, col + 16, row0);
+    }
+    w.in_flight = true;
+}
+__device__ __forceinline__ void epi_fwd_pair_lean2(const GemmParams& p, const CUtensorMap* tmAux, EpiWarp& w, int lane, int row0, int col, int next_col,
+                                                   float (&v)[32], volatile unsigned int* wd) {
+    if (!w.in_flight) epi_issue_aux_pair(tmAux, w, lane, row0, col);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = act_apply(ACT_LOGISTIC, v[e]);       // A: needs no dA — covers the TMA latency
+    ptx::mbar_wait(w.aux_bar, w.consumed & 1, wd, 0x600);
+    ++w.consumed;
+    w.in_flight = false;
+    float x[32];
+    stage_read_row<float, 16>(w.aux_buf, lane, *reinterpret_cast<float (*)[16]>(&x[0]));
+    stage_read_row<float, 16>(w.out_buf, lane, *reinterpret_cast<float (*)[16]>(&x[16]));
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = x[e] * (v[e] * (1.0f - v[e]));
+    // ---- A out
+    stage_write_row<float, 16>(w.aux_buf, lane, *reinterpret_cast<float (*)[16]>(&v[0]));
+    stage_write_row<float, 16>(w.out_buf, lane, *reinterpret_cast<float (*)[16]>(&v[16]));
+    __syncwarp();
+    stage_store_interior<float, 16>(w.aux_buf, lane, p.out0, p.ld_out0, row0, col);
+    stage_store_interior<float, 16>(w.out_buf, lane, p.out0, p.ld_out0, row0, col + 16);
+    __syncwarp();
+    // ---- db: lanes 0-15 sum the 16 columns of the first block, lanes 16-31 those of the second (rows visited in opposite order of
+    //      the row pair so that the two half-warps hit different banks)
+    stage_write_row<float, 16>(w.aux_buf, lane, *reinterpret_cast<float (*)[16]>(&x[0]));
+    stage_write_row<float, 16>(w.out_buf, lane, *reinterpret_cast<float (*)[16]>(&x[16]));
+    __syncwarp();
+    {
+        const int c = lane & 15, h = lane >> 4;
+        const uint32_t buf = h ? w.out_buf : w.aux_buf;
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int rr = r ^ h;                      // ((rr >> 1) & 3) == ((r >> 1) & 3): a compile-time swizzle term
+            part[r & 3] += ptx::lds32f(buf + rr * 64 + (((c >> 2) ^ ((r >> 1) & 3)) << 4) + (c & 3) * 4);
+        }
+        atomicAdd(p.colsum + col + lane, (part[0] + part[1]) + (part[2] + part[3]));
+    }
+    __syncwarp();
+    // ---- fp16 pair out
+    stage_write_row_f16pair<16>(w.aux_buf, lane, *reinterpret_cast<float (*)[16]>(&x[0]), w.out1_s);
+    stage_write_row_f16pair<16>(w.out_buf, lane, *reinterpret_cast<float (*)[16]>(&x[16]), w.out1_s);
+    __syncwarp();
+    stage_store_interior<__half, 16>(w.aux_buf, lane, p.out1, p.ld_out1, row0, col);
+    stage_store_interior<__half, 16>(w.aux_buf + 32 * 16 * 2, lane, p.out1b, p.ld_out1, row0, col);
+    stage_store_interior<__half, 16>(w.out_buf, lane, p.out1, p.ld_out1, row0, col + 16);
+    stage_store_interior<__half, 16>(w.out_buf + 32 * 16 * 2, lane, p.out1b, p.ld_out1, row0, col + 16);
+    __syncwarp();
+    if (next_col >= 0) epi_issue_aux_pair(tmAux, w, lane, row0, next_col);
+}
+
 // 8 fp32 values -> 8 x bf16(x) and 8 x bf16(x - trunc_tf32(x))   (operands of the two bf16 correction passes)
 __device__ __forceinline__ void split8_bf16(const uint4& x0, const uint4& x1, uint4& v16, uint4& l16) {
     const float f[8] = {__uint_as_float(x0.x), __uint_as_float(x0.y), __uint_as_float(x0.z), __uint_as_float(x0.w),
@@ -951,7 +1015,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
             constexpr int W = Cfg::EPI_W;
-            if (tma && epi_has_aux(p) && m0 + q * 32 < p.M && n0 + half * HC < p.N) {   // first aux block: requested before the K loop
+            const bool pair_epi = kPresplit && !(p.debug & 2) && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && p.out1_pair && p.colsum != nullptr &&
+                                  p.colsum_src == 2 && p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && m0 + q * 32 + 32 <= p.M &&
+                                  n0 + half * HC + HC <= p.N && !(p.debug & 1);
+            if (tma && pair_epi) {                                                      // paired epilogue: both dA blocks of the first pair
+                epi_issue_aux_pair(&tmAux, ew, lane, m0 + q * 32, n0 + half * HC);
+            } else if (tma && epi_has_aux(p) && m0 + q * 32 < p.M && n0 + half * HC < p.N) {   // first aux block: requested before the K loop
                 epi_issue_aux<float, W>(&tmAux, ew, lane, m0 + q * 32, n0 + half * HC);
                 if (lane > 0 && lane < HC / W && n0 + half * HC + lane * W < p.N)         // the other blocks: into L2 during the K loop
                     ptx::tma_prefetch_l2_2d(&tmAux, n0 + half * HC + lane * W, m0 + q * 32);
@@ -1027,7 +1096,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             if constexpr (kPresplit) {
-                if (lean) {
+                if (lean && !(p.debug & 2)) {     // the 32-column (paired) variant: the default
+#pragma unroll 1
+                    for (int c = 0; c < HC / 32; ++c) {
+                        const int col = n0 + half * HC + c * 32;
+                        epi_fwd_pair_lean2(p, &tmAux, ew, lane, row0, col, c + 1 < HC / 32 ? col + 32 : -1, *reinterpret_cast<float (*)[32]>(&sum[0]), wd);
+#pragma unroll
+                        for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];
+                    }
+                } else if (lean) {
 #pragma unroll 1
                     for (int c = 0; c < HC / 32; ++c) {
                         const int col = n0 + half * HC + c * 32;
