@@ -90,7 +90,7 @@ struct GemmParams {
     const float* out1_scale_ptr;  // device scalar, NULL = 1
     const float* out1_row_scale;  // [M], NULL = 1
     unsigned int* watchdog;   // mapped host memory, 2 words
-    int debug;                // TOPS_GEMM_DEBUG bit mask (A/B experiments): 1 = no specialised forward epilogue, 2 = its one-sub-block-at-a-time variant
+    int debug;                // TOPS_GEMM_DEBUG bit mask (A/B experiments): 1 = no specialised epilogues
 };
 
 template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
@@ -561,42 +561,11 @@ __device__ __forceinline__ void stage_store_interior(uint32_t buf, int lane, voi
     for (int k = 0; k < CPR; ++k) *reinterpret_cast<uint4*>(g0 + (long long)k * RPI * ld) = u[k];
 }
 
-// The hot epilogue of the F16X3 forward GEMM, written out without any of the generality of epi_block: one interior 32 x 16
-// sub-block of  A = logistic(acc + b),  dZ = dA * A (1 - A),  db += column sums of dZ,  (dZ1, dZ2) = fp16 pair of dZ * s.
+// The hot epilogue of the F16X3 forward GEMM, written out without any of the generality of epi_block: interior 32 x 16 sub-blocks of
+//   A = logistic(acc + b),  dZ = dA * A (1 - A),  db += column sums of dZ,  (dZ1, dZ2) = fp16 pair of dZ * s.
 // (The generic path costs ~680 instructions per sub-block — every epilogue variant, dtype and edge case is compiled into one
-// stream that no longer fits the instruction cache; this one is ~300.)  v: in = scaled accumulators + bias, lane = row.
-__device__ __forceinline__ void epi_fwd_pair_lean(const GemmParams& p, const CUtensorMap* tmAux, EpiWarp& w, int lane, int row0, int col, int next_col,
-                                                  float (&v)[16], volatile unsigned int* wd) {
-    if (!w.in_flight) epi_issue_aux<float, 16>(tmAux, w, lane, row0, col);
-    ptx::mbar_wait(w.aux_bar, w.consumed & 1, wd, 0x600);
-    ++w.consumed;
-    float x[16];
-    stage_read_row<float, 16>(w.aux_buf, lane, x);
-    __syncwarp();
-    w.in_flight = false;
-    if (next_col >= 0) epi_issue_aux<float, 16>(tmAux, w, lane, row0, next_col);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        const float a = act_apply(ACT_LOGISTIC, v[e]);
-        v[e] = a;
-        x[e] = x[e] * (a * (1.0f - a));
-    }
-    stage_write_row<float, 16>(w.out_buf, lane, v);
-    __syncwarp();
-    stage_store_interior<float, 16>(w.out_buf, lane, p.out0, p.ld_out0, row0, col);
-    __syncwarp();
-    stage_write_row<float, 16>(w.out_buf, lane, x);
-    __syncwarp();
-    stage_colsum<float, 16>(w.out_buf, lane, col, p.N, p.colsum);
-    __syncwarp();
-    stage_write_row_f16pair<16>(w.out_buf, lane, x, w.out1_s);
-    __syncwarp();
-    stage_store_interior<__half, 16>(w.out_buf, lane, p.out1, p.ld_out1, row0, col);
-    stage_store_interior<__half, 16>(w.out_buf + 32 * 16 * 2, lane, p.out1b, p.ld_out1, row0, col);
-    __syncwarp();
-}
-
-// The same epilogue on a PAIR of sub-blocks (32 columns) at a time: both staging blocks of the warp serve both sub-blocks in every
+// stream that no longer fits the instruction cache; this one is ~410.)  v: in = scaled accumulators + bias, lane = row.
+// It works on a PAIR of sub-blocks (32 columns) at a time: both staging blocks of the warp serve both sub-blocks in every
 // phase (dA in, A out, dZ for the column sums, the fp16 pair out), so a 32-column step has 7 warp-synchronised phases instead of
 // 14 and every phase has twice the independent work in flight (the 8 epilogue warps are latency-bound: 2 per scheduler).
 // The two dA blocks of the NEXT pair are requested (one mbarrier, 4 KiB) when this pair's last staged bytes have been read, and
@@ -1015,7 +984,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
             constexpr int W = Cfg::EPI_W;
-            const bool pair_epi = kPresplit && !(p.debug & 2) && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && p.out1_pair && p.colsum != nullptr &&
+            const bool pair_epi = kPresplit && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && p.out1_pair && p.colsum != nullptr &&
                                   p.colsum_src == 2 && p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && m0 + q * 32 + 32 <= p.M &&
                                   n0 + half * HC + HC <= p.N && !(p.debug & 1);
             if (tma && pair_epi) {                                                      // paired epilogue: both dA blocks of the first pair
@@ -1096,20 +1065,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             if constexpr (kPresplit) {
-                if (lean && !(p.debug & 2)) {     // the 32-column (paired) variant: the default
+                if (lean) {
 #pragma unroll 1
                     for (int c = 0; c < HC / 32; ++c) {
                         const int col = n0 + half * HC + c * 32;
                         epi_fwd_pair_lean2(p, &tmAux, ew, lane, row0, col, c + 1 < HC / 32 ? col + 32 : -1, *reinterpret_cast<float (*)[32]>(&sum[0]), wd);
-#pragma unroll
-                        for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];
-                    }
-                } else if (lean) {
-#pragma unroll 1
-                    for (int c = 0; c < HC / 32; ++c) {
-                        const int col = n0 + half * HC + c * 32;
-                        epi_fwd_pair_lean(p, &tmAux, ew, lane, row0, col, col + 16, *reinterpret_cast<float (*)[16]>(&sum[0]), wd);
-                        epi_fwd_pair_lean(p, &tmAux, ew, lane, row0, col + 16, c + 1 < HC / 32 ? col + 32 : -1, *reinterpret_cast<float (*)[16]>(&sum[16]), wd);
 #pragma unroll
                         for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];
                     }
