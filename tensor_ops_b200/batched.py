@@ -180,6 +180,10 @@ class BatchT:
 def _loop(fn: Callable[..., CuTensor], xs: List[BatchT]) -> BatchT:
     """Per-sample fallback: run `fn` on each sample's views and stack the results (device-side copies)."""
     BatchT.fallbacks += 1
+    if BatchT.fallbacks == 1:
+        import warnings
+        warnings.warn("tensor_ops_b200.batched: an op without a batched kernel is being evaluated one sample at a time "
+                      "(BatchT.fallbacks counts these); the result is exact but launch-bound", RuntimeWarning, stacklevel=3)
     B = next(x.B for x in xs if x.batched)
     outs = [fn(*[(x.t.row(b) if x.batched else x.t) for x in xs]) for b in range(B)]
     shape = outs[0].shape

@@ -244,6 +244,10 @@ int need_f32(tops_ctx* ctx, const tops_buf* x, const char* what) {
 }  // namespace
 struct SplitScope {
     tops_ctx* ctx; std::vector<tops_ctx::SplitEntry> entries; Tmp keep; bool owner;
+    // GEMM outputs whose max|.| the producing epilogue has already reduced (GemmCall::absmax_out): their split skips the absmax pass
+    struct KnownMax { const void* ptr; int64_t numel; unsigned* bits; };
+    std::vector<KnownMax> known_max;
+    bool track_max = false;          // set by calls whose GEMM outputs are operands of later GEMMs of the same call (the MLP)
     explicit SplitScope(tops_ctx* c) : ctx(c), owner(c->split_scope == nullptr) { if (owner) c->split_scope = this; }
     ~SplitScope() { if (owner) ctx->split_scope = nullptr; }
 };
@@ -262,9 +266,15 @@ int split_operand_f16(tops_ctx* ctx, const void* src, int64_t rows, int64_t cols
     TRY(alloc_buf(ctx, TOPS_BF16, 1, pd, &hi)); holder.keep(hi);
     TRY(alloc_buf(ctx, TOPS_BF16, 1, pd, &lo)); holder.keep(lo);
     TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &sc)); holder.keep(sc);   // {scale, 1/scale, absmax bits, -}
-    unsigned* mx = reinterpret_cast<unsigned*>(sc->data) + 2;
-    CUDA_TRY(ctx, cudaMemsetAsync(mx, 0, 4, ctx->stream));
-    k::absmax_bits(lc_of(ctx), (const float*)src, rows * cols, mx);
+    unsigned* mx = nullptr;
+    if (scope)
+        for (auto& km : scope->known_max)
+            if (km.ptr == src && km.numel == rows * cols) mx = km.bits;
+    if (mx == nullptr) {
+        mx = reinterpret_cast<unsigned*>(sc->data) + 2;
+        CUDA_TRY(ctx, cudaMemsetAsync(mx, 0, 4, ctx->stream));
+        k::absmax_bits(lc_of(ctx), (const float*)src, rows * cols, mx);
+    }
     k::split_f16_tensor_2d(lc_of(ctx), (const float*)src, rows, cols, ld, mx, hi->data, lo->data, (float*)sc->data);
     TRY(check_launch(ctx, "split_f16"));
     *out = tops_ctx::SplitEntry{src, rows, cols, hi->data, lo->data, ld, (float*)sc->data};
@@ -294,11 +304,22 @@ int run_gemm_f16x3(tops_ctx* ctx, const GemmCall& c0) {
     c.B = b.hi; c.B2 = b.lo; c.ldb = b.ld;
     c.B16 = c.Blo16 = nullptr;
     c.acc_scale_ptr = (const float*)sc->data;
+    SplitScope* scope = ctx->split_scope;
+    int max_done = 0;
+    if (scope && scope->track_max && (c.epi == EPI_BIAS_ACT || c.epi == EPI_MUL_DACT) && c.ld_out0 == c.N && c.out0_mc == nullptr) {
+        tops_buf* mxb = nullptr;                       // the epilogue leaves max|out0| here for the split of out0 later in this call
+        TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &mxb)); scope->keep.keep(mxb);
+        CUDA_TRY(ctx, cudaMemsetAsync(mxb->data, 0, 4, ctx->stream));
+        c.absmax_out = reinterpret_cast<unsigned*>(mxb->data);
+        c.absmax_done = &max_done;
+    }
     if (c.chunk_kb <= 0) {
         c.chunk_kb = c0.aux0 != nullptr ? ctx->f16x3_fwd_chunk_kb : ctx->f16x3_chunk_kb;
         if (c0.aux0 != nullptr) c.chunk_head_kb = ctx->f16x3_fwd_head_kb;
     }
-    return run_gemm(ctx, c);
+    const int r = run_gemm(ctx, c);
+    if (r == TOPS_OK && max_done) scope->known_max.push_back({c.out0, (int64_t)c.M * c.N, c.absmax_out});
+    return r;
 }
 
 int run_gemm(tops_ctx* ctx, GemmCall c) {
@@ -1562,6 +1583,7 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
     if (!dW || !db || !A_out || !loss_sum) return set_err(ctx, TOPS_ERR_INVALID, "mlp: NULL output slot");
     Tmp tmp;
     SplitScope split_scope_(ctx);   // F16X3: every tensor (activations, dZ, W) is split into its fp16 pair at most once per call
+    split_scope_.track_max = true;
     std::vector<const tops_buf*> acts_in(n);     // input of layer l
     std::vector<tops_buf*> Zs(n, nullptr);
     TRY(prep_out(ctx, loss_sum, TOPS_F32, 0, nullptr));
@@ -1593,7 +1615,9 @@ extern "C" int tops_mlp_fwd_grad(tops_ctx* ctx, int n, const tops_buf* const* W,
                          (float*)db[l]->data, &db_done[l], false, &wsp[l]));
         } else if (last && acts[l] == TOPS_ACT_SOFTMAX && loss == TOPS_LOSS_CROSS_ENTROPY) {
             TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], nullptr, &wsp[l]));
-            k::softmax_ce_rows(lc_of(ctx), (const float*)Zs[l]->data, (const float*)Y->data, (float*)A->data, (float*)dZ->data, lossp, B, d[1]);
+            CUDA_TRY(ctx, cudaMemsetAsync(db[l]->data, 0, sizeof(float) * (size_t)d[1], ctx->stream));
+            db_done[l] = k::softmax_ce_rows(lc_of(ctx), (const float*)Zs[l]->data, (const float*)Y->data, (float*)A->data, (float*)dZ->data, lossp, B, d[1],
+                                            (float*)db[l]->data) ? 1 : 0;   // narrow heads: db comes out of the same pass
             TRY(check_launch(ctx, "softmax_ce"));
         } else {
             TRY(mlp_layer_fwd(ctx, cur, W[l], b[l], acts[l], tmp, &Zs[l], A, &wsp[l]));

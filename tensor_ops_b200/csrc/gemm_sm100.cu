@@ -189,6 +189,13 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     const int total = tiles * p.split_k;
     const int grid = (total < ctas ? total : ctas) * cg;
     cudaError_t e;
+    // the MLP's hidden-layer GEMMs (forward / dA) have their own epilogue variant of the fp16-pair kernel (EV = 1): specialised
+    // interior-tile code for logistic, and max|out0| as a side output for every activation
+    if (c.dtype == 2 && cg == 2 && bn == 256 && c.major_a == MAJOR_K &&
+        ((c.epi == EPI_BIAS_ACT && c.major_b == MAJOR_K) || (c.epi == EPI_MUL_DACT && c.major_b == MAJOR_MN)))
+        passes = 5;
+    p.absmax_out = passes == 5 ? c.absmax_out : nullptr;
+    if (c.absmax_done) *c.absmax_done = p.absmax_out != nullptr ? 1 : 0;
     e = launch_any(c.dtype, cg, c.major_a, c.major_b, bn, passes, tm, p, grid, stream);
     if (e != cudaSuccess) {
         if (err && errlen) snprintf(err, errlen, "gemm launch: %s", cudaGetErrorString(e));

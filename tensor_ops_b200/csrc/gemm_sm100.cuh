@@ -89,6 +89,7 @@ struct GemmParams {
     void* out1b;
     const float* out1_scale_ptr;  // device scalar, NULL = 1
     const float* out1_row_scale;  // [M], NULL = 1
+    unsigned int* absmax_out;     // fp16-pair kernels, EV = 1: max over |out0| (float bits, atomicMax; caller zeroes); NULL = none
     unsigned int* watchdog;   // mapped host memory, 2 words
     int debug;                // TOPS_GEMM_DEBUG bit mask (A/B experiments): 1 = no specialised epilogues
 };
@@ -655,7 +656,11 @@ __device__ __forceinline__ void split4_bf16(const uint4& x, uint2& v8, uint2& l8
     }
 }
 
-template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
+// EV = 1 (fp16-pair kernels, A K-major): the epilogue variant of the MLP's hidden layers — specialised interior-tile code for
+//   EPI_BIAS_ACT / logistic (B K-major: the forward GEMM) and EPI_MUL_DACT / logistic (B MN-major: the dA GEMM) instead of the
+//   ffLayer step's paired forward epilogue and plain store (EV = 0).  Separate instantiations: the hot ffLayer kernels keep their
+//   register allocation and instruction footprint (both were measured to be sensitive to any code added next to them).
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG, int EV = 0>
 __global__ void __launch_bounds__((GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>::NUM_THREADS), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmAux,
                  const __grid_constant__ CUtensorMap tmB16, const __grid_constant__ CUtensorMap tmBlo16, const GemmParams p) {
@@ -984,7 +989,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
             constexpr int W = Cfg::EPI_W;
-            const bool pair_epi = kPresplit && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && p.out1_pair && p.colsum != nullptr &&
+            const bool pair_epi = kPresplit && EV == 0 && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && p.out1_pair && p.colsum != nullptr &&
                                   p.colsum_src == 2 && p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && m0 + q * 32 + 32 <= p.M &&
                                   n0 + half * HC + HC <= p.N && !(p.debug & 1);
             if (tma && pair_epi) {                                                      // paired epilogue: both dA blocks of the first pair
@@ -1020,7 +1025,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row0 = m0 + q * 32;
             const int row = row0 + lane;
             bool lean = false;
-            if constexpr (kPresplit) {   // hot case of the forward GEMM on an interior tile: the specialised sub-block code
+            if constexpr (kPresplit && EV == 0) {   // hot case of the forward GEMM on an interior tile: the specialised sub-block code
                 lean = tma && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && p.out1_pair && p.colsum != nullptr && p.colsum_src == 2 &&
                        p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && row0 + 32 <= p.M && n0 + half * HC + HC <= p.N && !(p.debug & 1);
             }
@@ -1030,7 +1035,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const float r = __ldg(p.row_scale + row);
                     rs *= p.row_scale_inv ? __frcp_rn(r) : r;   // powers of two: exact
                 }
-                if (lean) {   // bias folded into the same pass: 32 independent 16-byte broadcast loads instead of 4 per sub-block
+                bool lean_mlp = false;   // EV = 1: interior tile of a hidden MLP layer (forward or dA GEMM), logistic
+                if constexpr (kPresplit && EV == 1 && MA == MAJOR_K) {
+                    lean_mlp = tma && p.act == ACT_LOGISTIC && row0 + 32 <= p.M && n0 + half * HC + HC <= p.N && !(p.debug & 1) &&
+                               (MB == MAJOR_K ? (p.epi == EPI_BIAS_ACT && p.colsum == nullptr && p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)
+                                              : (p.epi == EPI_MUL_DACT && (p.colsum == nullptr || p.colsum_src == 1)));
+                    lean = lean_mlp;
+                }
+                if (lean && (EV == 0 || MB == MAJOR_K)) {   // bias folded into the same pass: 32 independent 16-byte broadcast loads instead of 4 per sub-block
                     const float4* b4p = reinterpret_cast<const float4*>(p.bias + n0 + half * HC);
 #pragma unroll
                     for (int g = 0; g < HC / 4; ++g) {
@@ -1050,7 +1062,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             bool lean_store = false;
             // (instantiated for the dX layout only — A K-major, B MN-major: in the variant that carries the specialised forward epilogue
             //  the extra code path costs registers — measured: 48 more bytes of spill and 8 % of the forward GEMM)
-            if constexpr (kPresplit && MA == MAJOR_K && MB == MAJOR_MN) {   // plain store of an interior tile (dX, gmul): stage + coalesced store, nothing else
+            if constexpr (kPresplit && EV == 0 && MA == MAJOR_K && MB == MAJOR_MN) {   // plain store of an interior tile (dX, gmul): stage + coalesced store, nothing else
                 lean_store = tma && p.epi == EPI_STORE && p.aux0 == nullptr && p.alpha == 1.0f && p.colsum == nullptr &&
                              row0 + 32 <= p.M && n0 + half * HC + HC <= p.N && !(p.debug & 1);
                 if (lean_store) {
@@ -1064,7 +1076,54 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     __syncwarp();
                 }
             }
-            if constexpr (kPresplit) {
+            if constexpr (kPresplit && EV == 1 && MA == MAJOR_K) {
+                if (lean) {
+                    float amax = 0.f;
+                    if constexpr (MB == MAJOR_K) {
+                        // A = logistic(acc + b): 16-column sub-blocks through the warp's two staging blocks in turn (one __syncwarp each)
+#pragma unroll
+                        for (int c = 0; c < HC / 16; ++c) {
+                            const uint32_t buf = (c & 1) ? ew.out_buf : ew.aux_buf;
+                            float (&v)[16] = *reinterpret_cast<float (*)[16]>(&sum[c * 16]);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) { v[e] = act_apply(ACT_LOGISTIC, v[e]); amax = fmaxf(amax, v[e]); }
+                            stage_write_row<float, 16>(buf, lane, v);
+                            __syncwarp();
+                            stage_store_interior<float, 16>(buf, lane, p.out0, p.ld_out0, row0, n0 + half * HC + c * 16);
+                        }
+                        __syncwarp();
+                    } else {
+                        // dZ = acc * a (1 - a), a = the layer's saved activation (aux, by TMA into aux_buf; the block after next is
+                        // requested as soon as this one has been read, its latency hides behind the math and the staged store)
+#pragma unroll
+                        for (int c = 0; c < HC / 16; ++c) {
+                            const int col = n0 + half * HC + c * 16;
+                            if (!ew.in_flight) epi_issue_aux<float, 16>(&tmAux, ew, lane, row0, col);
+                            ptx::mbar_wait(ew.aux_bar, ew.consumed & 1, wd, 0x600);
+                            ++ew.consumed;
+                            float x[16];
+                            stage_read_row<float, 16>(ew.aux_buf, lane, x);
+                            __syncwarp();                                          // also orders the previous sub-block's reads of out_buf
+                            ew.in_flight = false;
+                            if (c + 1 < HC / 16) epi_issue_aux<float, 16>(&tmAux, ew, lane, row0, col + 16);
+                            float (&v)[16] = *reinterpret_cast<float (*)[16]>(&sum[c * 16]);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) { v[e] *= x[e] * (1.0f - x[e]); amax = fmaxf(amax, fabsf(v[e])); }
+                            stage_write_row<float, 16>(ew.out_buf, lane, v);
+                            __syncwarp();
+                            stage_store_interior<float, 16>(ew.out_buf, lane, p.out0, p.ld_out0, row0, col);
+                            if (p.colsum != nullptr) stage_colsum<float, 16>(ew.out_buf, lane, col, p.N, p.colsum);   // db of the layer below
+                        }
+                        __syncwarp();
+                    }
+                    if (p.absmax_out != nullptr) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                        if (lane == 0) atomicMax(p.absmax_out, __float_as_uint(amax));
+                    }
+                }
+            }
+            if constexpr (kPresplit && EV == 0) {
                 if (lean) {
 #pragma unroll 1
                     for (int c = 0; c < HC / 32; ++c) {
@@ -1076,6 +1135,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             if (row0 < p.M && !lean && !lean_store) {
+                float out_amax = 0.f;
                 // ONE copy of the block code (the fused epilogue is large; unrolled four times it thrashes the instruction
                 // cache): always process sum[0..31], then rotate the register accumulators down by one block.
 #pragma unroll 1
@@ -1088,10 +1148,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             const bool more = (u + 1 < 32 / W || c + 1 < HC / 32) && col + W < p.N;
                             if (tma) epi_block<float, W, Cfg::EPI_SHARED>(p, &tmAux, ew, lane, row0, col, more ? col + W : -1, v, loss_acc, wd);
                             else if (row < p.M) epi_direct<W>(p, row, col, vec, v, loss_acc);
+                            if constexpr (kPresplit && EV == 1) {   // v now holds the out0 values: their |max| saves the consumer's absmax pass
+                                if (p.absmax_out != nullptr && row < p.M) {
+#pragma unroll
+                                    for (int e = 0; e < W; ++e) if (col + e < p.N) out_amax = fmaxf(out_amax, fabsf(v[e]));
+                                }
+                            }
                         }
                     }
 #pragma unroll
                     for (int e = 0; e < HC - 32; ++e) sum[e] = sum[e + 32];       // ... and the accumulators rotate afterwards
+                }
+                if constexpr (kPresplit && EV == 1) {
+                    if (p.absmax_out != nullptr) {                                  // one red per warp and tile (fire and forget)
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) out_amax = fmaxf(out_amax, __shfl_xor_sync(0xffffffffu, out_amax, o));
+                        if (lane == 0) atomicMax(p.absmax_out, __float_as_uint(out_amax));
+                    }
                 }
                 if (p.epi == EPI_ATOMIC && p.out0_mc != nullptr && n0 + half * HC < p.N)
                     mc_push_region_if_last(p, (tile * CG + (int)cta_rank) * 8 + (warp - 4), lane, row0, n0 + half * HC, min(HC, p.N - (n0 + half * HC)));

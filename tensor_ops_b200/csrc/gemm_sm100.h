@@ -21,6 +21,8 @@ struct GemmCall {
     const float* row_scale; int row_scale_inv;   // [M] device vector, NULL = 1
     // out1 as an fp16 pair for the next F16X3 GEMM: t = out1 * (*out1_scale_ptr) * out1_row_scale[m]; out1 <- fp16(t), out1b <- fp16(t - fp16(t))
     int out1_pair; void* out1b; const float* out1_scale_ptr; const float* out1_row_scale;
+    unsigned int* absmax_out;   // dtype 2, BIAS_ACT / MUL_DACT: atomicMax of the float bits of |out0| (zeroed by the caller); NULL = none
+    int* absmax_done;           // out: 1 when the launched variant produced absmax_out (pair kernel, 256-column tiles), else 0
     int epi, act;
     float alpha, beta;
     void* out0; long long ld_out0;

@@ -8,10 +8,10 @@
 
 namespace tops {
 
-template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG>
+template <typename T, int MA, int MB, int BN, int STAGES, int PASSES, int CG, int EV = 0>
 cudaError_t launch_one(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<T, MA, MB, BN, STAGES, PASSES, CG>;
-    auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES, CG>;
+    auto kern = gemm_umma_kernel<T, MA, MB, BN, STAGES, PASSES, CG, EV>;
     // opt in to > 48 KiB of dynamic shared memory: once per (instantiation, device) — the attribute is per device
     static unsigned long long attr_done_mask = 0;   // bit d = done on device d (racing threads at worst repeat the idempotent call)
     int dev = 0;
@@ -51,6 +51,9 @@ cudaError_t launch_cg(int bn, int passes, const CUtensorMap* tm, const GemmParam
         if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 6 : 5, 1, CG>(tm, p, grid, st);
         return launch_one<T, MA, MB, 256, CG == 2 ? 5 : 3, 1, CG>(tm, p, grid, st);
     } else if constexpr (std::is_same<T, __half>::value) {   // F16X3: (hi, lo) planes of both operands per stage: 2 * (128 + bn/CG) * 128 bytes
+        if constexpr (MA == MAJOR_K && CG == 2) {   // passes == 5: the MLP epilogue variant (EV = 1) of the 256-column pair kernel
+            if (passes == 5 && bn == 256) return launch_one<T, MA, MB, 256, 3, 4, CG, 1>(tm, p, grid, st);
+        }
         if (bn == 128) return launch_one<T, MA, MB, 128, CG == 2 ? 4 : 3, 4, CG>(tm, p, grid, st);
         return launch_one<T, MA, MB, 256, CG == 2 ? 3 : 2, 4, CG>(tm, p, grid, st);
     } else {
@@ -69,7 +72,7 @@ cudaError_t launch_major(int cg, int bn, int passes, const CUtensorMap* tm, cons
 #define TOPS_DEFINE_GEMM_VARIANT(NAME, MA, MB)                                                                                          \
     cudaError_t NAME(int dtype, int cg, int bn, int passes, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {    \
         if (dtype == 1) return launch_major<__nv_bfloat16, MA, MB>(cg, bn, 1, tm, p, grid, st);                                        \
-        if (dtype == 2) return launch_major<__half, MA, MB>(cg, bn, 4, tm, p, grid, st);                                               \
+        if (dtype == 2) return launch_major<__half, MA, MB>(cg, bn, passes, tm, p, grid, st);                                               \
         return launch_major<float, MA, MB>(cg, bn, passes, tm, p, grid, st);                                                           \
     }
 

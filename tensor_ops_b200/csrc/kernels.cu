@@ -449,10 +449,11 @@ __global__ void k_diag_extract(const float* __restrict__ a, float* __restrict__ 
 // ------------------------------------------------------------------ softmax / loss heads: one warp per row (sample)
 // mode 0: A = softmax(Z)    mode 1: dZ = softmax-VJP(Z, dA)    mode 2: fused softmax + crossEntropy (A, loss, dZ)
 template <int MODE>
-__global__ void k_softmax_rows(const float* __restrict__ Z, const float* __restrict__ aux, float* __restrict__ A, float* __restrict__ dZ, float* __restrict__ loss, int64_t rows, int64_t cols) {
+__global__ void k_softmax_rows(const float* __restrict__ Z, const float* __restrict__ aux, float* __restrict__ A, float* __restrict__ dZ, float* __restrict__ loss, int64_t rows, int64_t cols,
+                               float* __restrict__ colsum /* MODE 2, cols <= 32: += column sums of dZ (the head's db); NULL = none */) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float loss_acc = 0.f;
+    float loss_acc = 0.f, col_acc = 0.f;               // lane c always handles column c when cols <= 32
     for (int64_t r = warp0; r < rows; r += nwarps) {
         const float* z = Z + r * cols;
         float se = 0.f;
@@ -481,13 +482,83 @@ __global__ void k_softmax_rows(const float* __restrict__ Z, const float* __restr
                 const float e = __expf(z[c]);
                 float d;
                 if (MODE == 2) { const float a = e * rinv; d = -(aux[r * cols + c] / a); } else d = aux[r * cols + c];
-                dZ[r * cols + c] = (ds + d * rinv) * e;                        // duplicate's sumT [d1,d2], then map exp VJP
+                const float dz = (ds + d * rinv) * e;                          // duplicate's sumT [d1,d2], then map exp VJP
+                dZ[r * cols + c] = dz;
+                if (MODE == 2) col_acc += dz;
             }
         }
     }
-    if (MODE == 2 && loss) {
+    if (MODE == 2) {                                   // block-level sums first: one red per block for the loss and per column for db
+        __shared__ float sh[kThreads / 32][33];        // (same-address reds serialise in L2: one per warp cost ~20 us at 32768 rows)
         loss_acc = warp_sum(loss_acc);
-        if (lane == 0) atomicAdd(loss, loss_acc);
+        sh[threadIdx.x >> 5][lane] = col_acc;
+        if (lane == 0) sh[threadIdx.x >> 5][32] = loss_acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float s = 0.f, l = 0.f;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) { s += sh[w][threadIdx.x]; l += sh[w][32]; }
+            if (colsum != nullptr && threadIdx.x < cols) atomicAdd(colsum + threadIdx.x, s);
+            if (loss != nullptr && threadIdx.x == 0) atomicAdd(loss, l);
+        }
+    }
+}
+// softmax + crossEntropy head for few classes (cols <= CMAX): one THREAD per row — a warp per row leaves 22 of 32 lanes idle at
+// 10 classes and pays two shuffle reductions per row.  Same arithmetic as k_softmax_rows<2>; db = column sums of dZ.
+template <int CMAX>
+__global__ void k_softmax_ce_small(const float* __restrict__ Z, const float* __restrict__ Y, float* __restrict__ A, float* __restrict__ dZ,
+                                   float* __restrict__ loss, int64_t rows, int cols, float* __restrict__ colsum) {
+    const int lane = threadIdx.x & 31;
+    float loss_acc = 0.f, col_acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) col_acc[c] = 0.f;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        float e[CMAX], y[CMAX];
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            const bool ok = c < cols;
+            e[c] = ok ? __expf(Z[r * cols + c]) : 0.f;
+            y[c] = ok ? Y[r * cols + c] : 0.f;
+            se += e[c];
+        }
+        const float rinv = 1.0f / se;
+        float s = 0.f, d[CMAX];
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < cols) {
+                const float a = e[c] * rinv;
+                A[r * cols + c] = a;
+                loss_acc -= __logf(a) * y[c];
+                d[c] = -(y[c] / a);
+                s += d[c] * e[c];
+            } else d[c] = 0.f;
+        }
+        const float ds = -(rinv * rinv) * s;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < cols) {
+                const float dz = (ds + d[c] * rinv) * e[c];
+                dZ[r * cols + c] = dz;
+                col_acc[c] += dz;
+            }
+        }
+    }
+    __shared__ float sh[kThreads / 32][CMAX + 1];
+    loss_acc = warp_sum(loss_acc);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        const float v = warp_sum(col_acc[c]);
+        if (lane == 0) sh[threadIdx.x >> 5][c] = v;
+    }
+    if (lane == 0) sh[threadIdx.x >> 5][CMAX] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x <= CMAX) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += sh[w][threadIdx.x];
+        if (threadIdx.x == CMAX) { if (loss != nullptr) atomicAdd(loss, t); }
+        else if (colsum != nullptr && threadIdx.x < cols) atomicAdd(colsum + threadIdx.x, t);
     }
 }
 __global__ void k_loss_vjp(int loss, const float* __restrict__ A, const float* __restrict__ Y, float* __restrict__ dA, float* __restrict__ out, int64_t n) {
@@ -1009,15 +1080,21 @@ void diag_extract(const LaunchCtx& lc, const float* a, float* out, int64_t n, in
 
 void softmax_rows(const LaunchCtx& lc, const float* Z, float* A, int64_t rows, int64_t cols) {
     if (rows * cols <= 0) return;
-    k_softmax_rows<0><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, nullptr, A, nullptr, nullptr, rows, cols); count(lc);
+    k_softmax_rows<0><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, nullptr, A, nullptr, nullptr, rows, cols, nullptr); count(lc);
 }
 void softmax_vjp_rows(const LaunchCtx& lc, const float* Z, const float* dA, float* dZ, int64_t rows, int64_t cols) {
     if (rows * cols <= 0) return;
-    k_softmax_rows<1><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, dA, nullptr, dZ, nullptr, rows, cols); count(lc);
+    k_softmax_rows<1><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, dA, nullptr, dZ, nullptr, rows, cols, nullptr); count(lc);
 }
-void softmax_ce_rows(const LaunchCtx& lc, const float* Z, const float* Y, float* A, float* dZ, float* loss, int64_t rows, int64_t cols) {
-    if (rows * cols <= 0) return;
-    k_softmax_rows<2><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, Y, A, dZ, loss, rows, cols); count(lc);
+bool softmax_ce_rows(const LaunchCtx& lc, const float* Z, const float* Y, float* A, float* dZ, float* loss, int64_t rows, int64_t cols, float* db) {
+    if (rows * cols <= 0) return false;
+    const bool fuse_db = db != nullptr && cols <= 32;
+    if (cols <= 16) {
+        k_softmax_ce_small<16><<<grid_for(lc, rows, kThreads, 2), kThreads, 0, lc.stream>>>(Z, Y, A, dZ, loss, rows, (int)cols, fuse_db ? db : nullptr); count(lc);
+        return fuse_db;
+    }
+    k_softmax_rows<2><<<grid_for(lc, rows * 32, kThreads, 4), kThreads, 0, lc.stream>>>(Z, Y, A, dZ, loss, rows, cols, fuse_db ? db : nullptr); count(lc);
+    return fuse_db;
 }
 void loss_vjp(const LaunchCtx& lc, int loss, const float* A, const float* Y, float* dA, float* loss_out, int64_t n) {
     if (n <= 0) return;

@@ -85,7 +85,8 @@ void softmax_rows(const LaunchCtx&, const float* Z, float* A, int64_t rows, int6
 // dZ = VJP of the reference softmax TOp given dA (A not needed: recomputed from Z like the reference's closures)
 void softmax_vjp_rows(const LaunchCtx&, const float* Z, const float* dA, float* dZ, int64_t rows, int64_t cols);
 // fused softmax + crossEntropy head: A = softmax(Z); loss += -sum(log A * Y); dZ = VJP chain of crossEntropy∘softmax
-void softmax_ce_rows(const LaunchCtx&, const float* Z, const float* Y, float* A, float* dZ, float* loss, int64_t rows, int64_t cols);
+// db (nullable, PRE-ZEROED [cols]): column sums of dZ fused in when cols <= 32 (the MNIST-style head); returns whether they were produced
+bool softmax_ce_rows(const LaunchCtx&, const float* Z, const float* Y, float* A, float* dZ, float* loss, int64_t rows, int64_t cols, float* db = nullptr);
 // loss VJPs on activations: squaredError dA = -2 (Y - A), loss += sum (Y-A)^2 ; crossEntropy dA = -Y / A, loss += -sum(log A * Y)
 void loss_vjp(const LaunchCtx&, int loss, const float* A, const float* Y, float* dA, float* loss_out, int64_t n);
 
