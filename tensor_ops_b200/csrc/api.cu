@@ -284,6 +284,20 @@ int split_operand_f16(tops_ctx* ctx, const void* src, int64_t rows, int64_t cols
 
 int run_gemm(tops_ctx* ctx, GemmCall c);
 
+// Inside a call that tracks them (SplitScope::track_max): give the GEMM a zeroed slot where its epilogue leaves max|out0|, so that the
+// fp16-pair split of out0 later in the same call needs no absmax pass.  *done is set by the launcher when the variant produced it.
+int want_out_max(tops_ctx* ctx, GemmCall& c, int* done) {
+    SplitScope* scope = ctx->split_scope;
+    if (!(scope && scope->track_max && (c.epi == EPI_BIAS_ACT || c.epi == EPI_MUL_DACT) && c.ld_out0 == c.N && c.out0_mc == nullptr)) return TOPS_OK;
+    int64_t sd[1] = {1};
+    tops_buf* mxb = nullptr;
+    TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &mxb)); scope->keep.keep(mxb);
+    CUDA_TRY(ctx, cudaMemsetAsync(mxb->data, 0, 4, ctx->stream));
+    c.absmax_out = reinterpret_cast<unsigned*>(mxb->data);
+    c.absmax_done = done;
+    return TOPS_OK;
+}
+
 // fp32 operands under TOPS_PREC_F16X3: split both (cached per call) and run the fp16-pair kernel
 int run_gemm_f16x3(tops_ctx* ctx, const GemmCall& c0) {
     if (c0.dtype != 0 || c0.io_bf16 || c0.M <= 0 || c0.N <= 0 || c0.K <= 0) return kF16X3Fallback;
@@ -306,13 +320,7 @@ int run_gemm_f16x3(tops_ctx* ctx, const GemmCall& c0) {
     c.acc_scale_ptr = (const float*)sc->data;
     SplitScope* scope = ctx->split_scope;
     int max_done = 0;
-    if (scope && scope->track_max && (c.epi == EPI_BIAS_ACT || c.epi == EPI_MUL_DACT) && c.ld_out0 == c.N && c.out0_mc == nullptr) {
-        tops_buf* mxb = nullptr;                       // the epilogue leaves max|out0| here for the split of out0 later in this call
-        TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &mxb)); scope->keep.keep(mxb);
-        CUDA_TRY(ctx, cudaMemsetAsync(mxb->data, 0, 4, ctx->stream));
-        c.absmax_out = reinterpret_cast<unsigned*>(mxb->data);
-        c.absmax_done = &max_done;
-    }
+    TRY(want_out_max(ctx, c, &max_done));
     if (c.chunk_kb <= 0) {
         c.chunk_kb = c0.aux0 != nullptr ? ctx->f16x3_fwd_chunk_kb : ctx->f16x3_chunk_kb;
         if (c0.aux0 != nullptr) c.chunk_head_kb = ctx->f16x3_fwd_head_kb;
@@ -325,6 +333,19 @@ int run_gemm_f16x3(tops_ctx* ctx, const GemmCall& c0) {
 int run_gemm(tops_ctx* ctx, GemmCall c) {
     if (c.colsum_fused) *c.colsum_fused = 0;
     if (c.M <= 0 || c.N <= 0) return TOPS_OK;
+    // One tiny dimension (an MLP's output layer): streaming fp32 CUDA-core kernels — HBM-bound work the tensor-core tiles and the
+    // operand splits would only slow down.  FP32_SIMT keeps its single reference kernel.
+    if (ctx->precision != TOPS_PREC_FP32_SIMT && k::gemm_skinny_kind(c) != 0) {
+        ProfScope prof_(ctx, c.tag ? c.tag : "gemm", 2.0 * c.M * c.N * (double)c.K,
+                        4.0 * ((double)c.M * c.K + (double)c.N * c.K + (double)c.M * c.N * ((c.aux0 ? 1 : 0) + 1)));
+        if (c.epi == EPI_ATOMIC && !c.accumulate) CUDA_TRY(ctx, cudaMemsetAsync(c.out0, 0, sizeof(float) * (size_t)c.M * (size_t)c.ld_out0, ctx->stream));
+        int max_done = 0;
+        TRY(want_out_max(ctx, c, &max_done));
+        const int r = k::gemm_skinny(lc_of(ctx), c, c.colsum_fused, &max_done);
+        if (r < 0) return set_err(ctx, TOPS_ERR_CUDA, "skinny gemm launch failed (%d)", -r);
+        if (max_done) ctx->split_scope->known_max.push_back({c.out0, (int64_t)c.M * c.N, c.absmax_out});
+        return TOPS_OK;
+    }
     // F16X3 with fp32 operands: split them into fp16 pairs (comes back here with dtype 2).  Small products (< 2 GFLOP) are not worth
     // the split passes: they take the in-kernel TF32 + bf16-correction route below when TMA can describe them as they are.
     const bool f16x3 = c.dtype == 0 && ctx->precision == TOPS_PREC_F16X3;

@@ -1129,5 +1129,391 @@ int gemm_simt(const LaunchCtx& lc, const GemmCall& c) {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
+
+// ---------------------------------------------------------------------- skinny GEMMs: one of M, N, K is <= 16
+// The MLP's output layer (10 classes at BASELINE configs[2]) gives three products with one tiny dimension: 5 FLOP per byte of the
+// large operand, i.e. HBM-bound by a factor > 20 on this machine.  A 128 x 256 tensor-core tile would be 4-6 % full and the fp16
+// pair splits of the operands would move more bytes than the product itself, so these run on the CUDA cores in plain fp32 (exact
+// products, fp32 accumulation) at the speed the large operand streams:
+//   skinny-K  out[s,f]  = epi( sum_{j<n} T[s,j] W[j,f] )        (dA of the output layer: EPI_MUL_DACT, + db / max|out| side outputs)
+//   skinny-M  out[j,f] += alpha sum_s T[s,j] F[s,f]             (dW of the output layer: EPI_ATOMIC)
+//   skinny-N  out[s,j]  = epi( sum_k X[s,k] W[j,k] )            (forward of the output layer: EPI_BIAS_ACT)
+namespace {
+constexpr int kSkinnyRows = 256;    // rows of the thin operand staged per pass (padded to 16 floats each: 16 KiB)
+constexpr int kSkinnyThreads = 512;
+constexpr int kSkinnyBatch = 4;     // rows per batch; the next batch's 16-byte loads of the wide operand are in flight while this one is used
+
+__device__ __forceinline__ void block_absmax_commit(float amax, unsigned int* out) {
+    if (out == nullptr) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(amax));
+}
+
+// thin operand rows [r0, r0 + nrows) -> sT[row][16] (zero padded), coalesced
+__device__ __forceinline__ void skinny_stage_thin(float (*sT)[16], const float* __restrict__ T, long long ldt, int64_t r0, int nrows, int n) {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
+    for (int i = tid; i < nrows * 16; i += nthreads) {
+        const int r = i >> 4, j = i & 15;
+        sT[r][j] = j < n ? __ldg(T + (r0 + r) * ldt + j) : 0.f;
+    }
+}
+template <int VEC> struct SkinnyVec { float v[VEC]; };
+template <int VEC> __device__ __forceinline__ SkinnyVec<VEC> skinny_ld(const float* p) {
+    SkinnyVec<VEC> r;
+    if constexpr (VEC == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else r.v[0] = __ldg(p);
+    return r;
+}
+template <int VEC> __device__ __forceinline__ void skinny_st(float* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else *p = v[0];
+}
+
+// blockDim = (TX column threads, TY row lanes), 512 threads; thread = VEC consecutive columns; NJ = n rounded up to a multiple of 4.
+// Row lane y takes rows y, y + TY, ... of a staged pass, kSkinnyBatch at a time: the batch's loads of the wide operand are issued
+// before any of them is used.
+template <int VEC, int NJ, bool LOGI>   // LOGI: EPI_MUL_DACT with the logistic derivative a (1 - a), resolved at compile time
+__global__ void __launch_bounds__(kSkinnyThreads) k_skinny_k(const float* __restrict__ T, long long ldt, const float* __restrict__ W, long long ldw, GemmParams p, int rows_per_cta) {
+    __shared__ __align__(16) float sT[kSkinnyRows][16];
+    __shared__ float sCol[kSkinnyThreads * VEC];     // column-sum partials of the row lanes, reduced before the reds
+    const int f0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const bool col_ok = f0 < p.N;            // VEC == 4: N % 4 == 0, so a thread is all in or all out
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_cta, r_end = min((int64_t)p.M, r_begin + rows_per_cta);
+    const float* aux = reinterpret_cast<const float*>(p.aux0);
+    float* out = reinterpret_cast<float*>(p.out0);
+    const bool dact = p.epi == EPI_MUL_DACT;
+    const int TY = blockDim.y;
+    // the wide operand's loads run one batch ahead of the arithmetic (rows r_begin + y + i * TY of the CTA's slice, in slice order)
+    const int64_t stride = (int64_t)kSkinnyBatch * TY;
+    SkinnyVec<VEC> nxt[kSkinnyBatch];
+    auto fetch = [&](int64_t row0) {
+        if (!dact || !col_ok) return;
+#pragma unroll
+        for (int i = 0; i < kSkinnyBatch; ++i)
+            if (row0 + i * TY < r_end) nxt[i] = skinny_ld<VEC>(aux + (row0 + i * TY) * p.ld_aux0 + f0);
+    };
+    fetch(r_begin + threadIdx.y);
+    float w[NJ][VEC];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[j][v] = (col_ok && j < p.K) ? __ldg(W + (long long)j * ldw + f0 + v) : 0.f;
+    float csum[VEC], amax = 0.f;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) csum[v] = 0.f;
+    static_assert(kSkinnyRows % kSkinnyBatch == 0, "a staged pass holds whole batches");
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += kSkinnyRows) {
+        const int nrows = (int)min((int64_t)kSkinnyRows, r_end - r0);
+        __syncthreads();
+        skinny_stage_thin(sT, T, ldt, r0, nrows, p.K);
+        __syncthreads();
+        if (!col_ok) continue;
+        // kSkinnyRows is a multiple of kSkinnyBatch * TY (TY | 16), so the batches of consecutive passes continue the same sequence
+        for (int rb = threadIdx.y; rb < nrows; rb += (int)stride) {
+            SkinnyVec<VEC> a[kSkinnyBatch];
+#pragma unroll
+            for (int i = 0; i < kSkinnyBatch; ++i) a[i] = nxt[i];
+            fetch(r0 + rb + stride);
+#pragma unroll
+            for (int i = 0; i < kSkinnyBatch; ++i) {
+                const int r = rb + i * TY;
+                if (r >= nrows) break;
+                float acc[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < NJ / 4; ++j4) {
+                    const float4 t = *reinterpret_cast<const float4*>(&sT[r][j4 * 4]);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        acc[v] = fmaf(t.x, w[j4 * 4][v], acc[v]); acc[v] = fmaf(t.y, w[j4 * 4 + 1][v], acc[v]);
+                        acc[v] = fmaf(t.z, w[j4 * 4 + 2][v], acc[v]); acc[v] = fmaf(t.w, w[j4 * 4 + 3][v], acc[v]);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if constexpr (LOGI) acc[v] *= a[i].v[v] * (1.0f - a[i].v[v]);
+                    else acc[v] = dact ? acc[v] * act_deriv_from_out(p.act, a[i].v[v]) : acc[v] * p.alpha;
+                    csum[v] += acc[v]; amax = fmaxf(amax, fabsf(acc[v]));
+                }
+                skinny_st<VEC>(out + (r0 + r) * p.ld_out0 + f0, acc);
+            }
+        }
+    }
+    if (p.colsum != nullptr) {               // uniform across the block
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sCol[(threadIdx.y * blockDim.x + threadIdx.x) * VEC + v] = csum[v];
+        __syncthreads();
+        if (threadIdx.y == 0 && col_ok) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float t = 0.f;
+                for (int y = 0; y < TY; ++y) t += sCol[(y * blockDim.x + threadIdx.x) * VEC + v];
+                atomicAdd(p.colsum + f0 + v, t);
+            }
+        }
+    }
+    block_absmax_commit(amax, p.absmax_out);
+}
+
+template <int VEC, int NJ>
+__global__ void __launch_bounds__(kSkinnyThreads) k_skinny_m(const float* __restrict__ T, long long ldt, const float* __restrict__ F, long long ldf, GemmParams p, int rows_per_cta) {
+    // one buffer, two lives: the staged thin rows during the sweep, then the row lanes' partial sums (4 thin columns at a time)
+    __shared__ __align__(16) float sbuf[4 * kSkinnyThreads * VEC > kSkinnyRows * 16 ? 4 * kSkinnyThreads * VEC : kSkinnyRows * 16];
+    float (*sT)[16] = reinterpret_cast<float (*)[16]>(sbuf);
+    const int f0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const bool col_ok = f0 < p.N;
+    const int TY = blockDim.y;
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_cta, r_end = min((int64_t)p.K, r_begin + rows_per_cta);   // the contraction runs over rows
+    const int64_t stride = (int64_t)kSkinnyBatch * TY;
+    SkinnyVec<VEC> nxt[kSkinnyBatch];
+    auto fetch = [&](int64_t row0) {
+        if (!col_ok) return;
+#pragma unroll
+        for (int i = 0; i < kSkinnyBatch; ++i)
+            if (row0 + i * TY < r_end) nxt[i] = skinny_ld<VEC>(F + (row0 + i * TY) * ldf + f0);
+    };
+    fetch(r_begin + threadIdx.y);
+    float acc[NJ][VEC];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[j][v] = 0.f;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += kSkinnyRows) {
+        const int nrows = (int)min((int64_t)kSkinnyRows, r_end - r0);
+        __syncthreads();
+        skinny_stage_thin(sT, T, ldt, r0, nrows, p.M);
+        __syncthreads();
+        if (!col_ok) continue;
+        for (int rb = threadIdx.y; rb < nrows; rb += (int)stride) {
+            SkinnyVec<VEC> x[kSkinnyBatch];
+#pragma unroll
+            for (int i = 0; i < kSkinnyBatch; ++i) x[i] = nxt[i];
+            fetch(r0 + rb + stride);
+#pragma unroll
+            for (int i = 0; i < kSkinnyBatch; ++i) {
+                const int r = rb + i * TY;
+                if (r >= nrows) break;
+#pragma unroll
+                for (int j4 = 0; j4 < NJ / 4; ++j4) {
+                    const float4 t = *reinterpret_cast<const float4*>(&sT[r][j4 * 4]);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        acc[j4 * 4][v] = fmaf(t.x, x[i].v[v], acc[j4 * 4][v]); acc[j4 * 4 + 1][v] = fmaf(t.y, x[i].v[v], acc[j4 * 4 + 1][v]);
+                        acc[j4 * 4 + 2][v] = fmaf(t.z, x[i].v[v], acc[j4 * 4 + 2][v]); acc[j4 * 4 + 3][v] = fmaf(t.w, x[i].v[v], acc[j4 * 4 + 3][v]);
+                    }
+                }
+            }
+        }
+    }
+    float* out = reinterpret_cast<float*>(p.out0);
+    const int slot = (threadIdx.y * blockDim.x + threadIdx.x) * VEC;
+#pragma unroll
+    for (int j4 = 0; j4 < NJ / 4; ++j4) {
+        if (j4 * 4 >= p.M) break;             // uniform
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sbuf[jj * kSkinnyThreads * VEC + slot + v] = acc[j4 * 4 + jj][v];
+        __syncthreads();
+        // 4 thin columns x (TX * VEC) wide columns to finish: spread over all row lanes (lane y takes thin column y % 4 ... )
+        for (int jj = threadIdx.y; jj < 4; jj += TY) {
+            const int j = j4 * 4 + jj;
+            if (j < p.M && col_ok) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    float t = 0.f;
+                    for (int y = 0; y < TY; ++y) t += sbuf[jj * kSkinnyThreads * VEC + (y * blockDim.x + threadIdx.x) * VEC + v];
+                    atomicAdd(out + (long long)j * p.ld_out0 + f0 + v, p.alpha * t);
+                }
+            }
+        }
+    }
+}
+
+// halving exchange over the 8 lanes that share a row: lanes whose bit H/2... see k_skinny_n
+template <int H, int BIT> __device__ __forceinline__ void skinny_halve(float (&a)[16], int lane) {
+    const bool upper = (lane & BIT) != 0;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float send = upper ? a[j] : a[j + H];
+        const float keep = upper ? a[j + H] : a[j];
+        a[j] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
+    }
+}
+
+// A warp works on 16 rows: lane = (row quarter q = lane / 8, k lane kl = lane % 8) handles rows q, q + 4, q + 8, q + 12 of the
+// group and, of every 8 * VEC-wide chunk of K, the VEC elements at kl * VEC — so a warp load instruction reads four 128-byte row
+// segments and the matching pieces of W (shared memory, 128 contiguous bytes broadcast to the four quarters) serve four rows per
+// read.  The 8 partial sums of a row meet in a halving exchange (14 shuffles per 16 columns); lane kl ends with columns 2kl, 2kl+1.
+template <int VEC, int NJ>
+__global__ void __launch_bounds__(256) k_skinny_n(const float* __restrict__ X, long long ldx, const float* __restrict__ W, long long ldw, GemmParams p) {
+    extern __shared__ __align__(16) float sW[];
+    const int ldk = (p.K + 3) / 4 * 4 + 4;
+    for (int j = 0; j < NJ; ++j)                                     // rows N..NJ-1 are zero: the inner loops run over all NJ
+        for (int k = threadIdx.x; k < ldk; k += blockDim.x) sW[j * ldk + k] = (j < p.N && k < p.K) ? __ldg(W + (long long)j * ldw + k) : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, q = lane >> 3, kl = lane & 7;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float* out = reinterpret_cast<float*>(p.out0);
+    const int j0 = 2 * kl;
+    const bool biased = p.epi == EPI_BIAS_ACT;
+    const float b0 = (biased && p.bias != nullptr && j0 < p.N) ? __ldg(p.bias + j0) : 0.f;
+    const float b1 = (biased && p.bias != nullptr && j0 + 1 < p.N) ? __ldg(p.bias + j0 + 1) : 0.f;
+    float amax = 0.f;
+    constexpr int R = 4, CH = 8 * VEC;
+    for (int64_t s0 = warp * 16; s0 < p.M; s0 += nwarps * 16) {
+        float acc[R][16];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[r][j] = 0.f;
+        const float* xrow[R];
+        bool ok[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { const int64_t row = s0 + q + 4 * r; ok[r] = row < p.M; xrow[r] = X + (ok[r] ? row : 0) * ldx + kl * VEC; }
+#pragma unroll 2
+        for (int k0 = 0; k0 < p.K; k0 += CH) {
+            const bool kin = k0 + kl * VEC < p.K;
+            SkinnyVec<VEC> x[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (ok[r] && kin) x[r] = skinny_ld<VEC>(xrow[r] + k0);
+                else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) x[r].v[v] = 0.f;
+                }
+            }
+            const float* wp = sW + k0 + kl * VEC;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                float wv[VEC];
+                if constexpr (VEC == 4) {   // (the last chunk of a K that is not a multiple of 32 ends inside the row: lanes beyond it read nothing)
+                    const float4 t = kin ? *reinterpret_cast<const float4*>(wp + j * ldk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+                } else wv[0] = kin ? wp[j * ldk] : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[r][j] = fmaf(x[r].v[v], wv[v], acc[r][j]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            skinny_halve<8, 4>(acc[r], lane); skinny_halve<4, 2>(acc[r], lane); skinny_halve<2, 1>(acc[r], lane);
+            float v0 = acc[r][0], v1 = acc[r][1];
+            if (biased) { v0 = act_apply(p.act, v0 + b0); v1 = act_apply(p.act, v1 + b1); }
+            else { v0 *= p.alpha; v1 *= p.alpha; }
+            if (ok[r]) {
+                float* o = out + (s0 + q + 4 * r) * p.ld_out0 + j0;
+                if (j0 < p.N) { o[0] = v0; amax = fmaxf(amax, fabsf(v0)); }
+                if (j0 + 1 < p.N) { o[1] = v1; amax = fmaxf(amax, fabsf(v1)); }
+            }
+        }
+    }
+    block_absmax_commit(amax, p.absmax_out);
+}
+}  // namespace
+
+size_t skinny_n_smem(int N, int K) { return sizeof(float) * (size_t)((N + 3) / 4 * 4) * ((size_t)(K + 3) / 4 * 4 + 4); }
+constexpr size_t kSkinnyNSmemMax = 200 * 1024;   // K <= 3196
+
+// 0 = not a skinny product, 1 = skinny-K, 2 = skinny-M, 3 = skinny-N
+int gemm_skinny_kind(const GemmCall& c) {
+    if (c.dtype != 0 || c.io_bf16 || c.M <= 0 || c.N <= 0 || c.K <= 0 || c.out0_mc != nullptr) return 0;
+    if (c.K <= 16 && c.major_a == MAJOR_K && c.major_b == MAJOR_MN && ((c.epi == EPI_STORE && c.aux0 == nullptr) || c.epi == EPI_MUL_DACT) &&
+        (c.colsum == nullptr || c.colsum_src == 0 || c.colsum_src == 1)) return 1;
+    if (c.M <= 16 && c.major_a == MAJOR_MN && c.major_b == MAJOR_MN && c.epi == EPI_ATOMIC) return 2;
+    if (c.N <= 16 && c.major_a == MAJOR_K && c.major_b == MAJOR_K && ((c.epi == EPI_STORE && c.aux0 == nullptr) || c.epi == EPI_BIAS_ACT) &&
+        (c.colsum == nullptr || c.colsum_src == 0) && skinny_n_smem(c.N, c.K) <= kSkinnyNSmemMax) return 3;
+    return 0;
+}
+
+int gemm_skinny(const LaunchCtx& lc, const GemmCall& c, int* colsum_fused, int* absmax_done) {
+    const int kind = gemm_skinny_kind(c);
+    if (kind == 0) return 0;
+    const float* A = reinterpret_cast<const float*>(c.A);
+    const float* B = reinterpret_cast<const float*>(c.B);
+    GemmParams p{};
+    p.M = c.M; p.N = c.N; p.K = c.K; p.epi = c.epi; p.act = c.act; p.alpha = c.alpha;
+    p.out0 = c.out0; p.ld_out0 = c.ld_out0; p.aux0 = c.aux0; p.ld_aux0 = c.ld_aux0; p.bias = c.bias;
+    auto a16 = [](const void* q, long long ld) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && ld % 4 == 0; };
+    // columns of the wide operand per thread / threads per row / row lanes, and the row slices of a grid of ~4 CTAs per SM
+    auto shape = [&](int ncols, int64_t rows, bool vec, int ctas_per_sm, dim3& block, dim3& grid, int& rows_per_cta) {
+        const int per = vec ? 4 : 1;
+        int tx = (ncols + per - 1) / per;
+        tx = tx >= kSkinnyThreads ? kSkinnyThreads : (tx + 31) / 32 * 32;
+        while (kSkinnyThreads % tx) tx += 32;
+        const int ty = kSkinnyThreads / tx;
+        block = dim3(tx, ty);
+        const int gx = (ncols + tx * per - 1) / (tx * per);
+        int64_t gy = ((int64_t)lc.num_sms * ctas_per_sm + gx - 1) / gx;
+        const int64_t max_gy = (rows + 4 * ty - 1) / (4 * ty);          // at least 4 rows per row lane
+        if (gy > max_gy) gy = max_gy;
+        if (gy < 1) gy = 1;
+        if (gy > 65535) gy = 65535;
+        rows_per_cta = (int)((rows + gy - 1) / gy);
+        grid = dim3(gx, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+    };
+    if (kind == 1) {
+        const bool vec = c.N % 4 == 0 && a16(c.B, c.ldb) && a16(c.out0, c.ld_out0) && (c.epi != EPI_MUL_DACT || a16(c.aux0, c.ld_aux0));
+        p.colsum = c.colsum_src == 1 ? c.colsum : nullptr; p.colsum_src = c.colsum_src;
+        p.absmax_out = c.absmax_out;
+        dim3 block, grid; int rpc;
+        shape(c.N, c.M, vec, 1, block, grid, rpc);
+        const int nj = (c.K + 3) / 4;
+#define TOPS_SKINNY_K(V, L) \
+        switch (nj) { case 1: k_skinny_k<V, 4, L><<<grid, block, 0, lc.stream>>>(A, c.lda, B, c.ldb, p, rpc); break; \
+                      case 2: k_skinny_k<V, 8, L><<<grid, block, 0, lc.stream>>>(A, c.lda, B, c.ldb, p, rpc); break; \
+                      case 3: k_skinny_k<V, 12, L><<<grid, block, 0, lc.stream>>>(A, c.lda, B, c.ldb, p, rpc); break; \
+                      default: k_skinny_k<V, 16, L><<<grid, block, 0, lc.stream>>>(A, c.lda, B, c.ldb, p, rpc); break; }
+        const bool logi = c.epi == EPI_MUL_DACT && c.act == ACT_LOGISTIC;
+        if (vec) { if (logi) { TOPS_SKINNY_K(4, true) } else { TOPS_SKINNY_K(4, false) } }
+        else { if (logi) { TOPS_SKINNY_K(1, true) } else { TOPS_SKINNY_K(1, false) } }
+#undef TOPS_SKINNY_K
+        count(lc);
+        if (colsum_fused) *colsum_fused = p.colsum != nullptr ? 1 : 0;
+        if (absmax_done) *absmax_done = p.absmax_out != nullptr ? 1 : 0;
+    } else if (kind == 2) {
+        const bool vec = c.N % 4 == 0 && a16(c.B, c.ldb);
+        dim3 block, grid; int rpc;
+        shape(c.N, c.K, vec, 1, block, grid, rpc);   // few CTAs: every one ends with M x columns reds
+        const int nj = (c.M + 3) / 4;
+#define TOPS_SKINNY_M(V) \
+        switch (nj) { case 1: k_skinny_m<V, 4><<<grid, block, 0, lc.stream>>>(A, c.lda, B, c.ldb, p, rpc); break; \
+                      case 2: k_skinny_m<V, 8><<<grid, block, 0, lc.stream>>>(A, c.lda, B, c.ldb, p, rpc); break; \
+                      case 3: k_skinny_m<V, 12><<<grid, block, 0, lc.stream>>>(A, c.lda, B, c.ldb, p, rpc); break; \
+                      default: k_skinny_m<V, 16><<<grid, block, 0, lc.stream>>>(A, c.lda, B, c.ldb, p, rpc); break; }
+        if (vec) { TOPS_SKINNY_M(4) } else { TOPS_SKINNY_M(1) }
+#undef TOPS_SKINNY_M
+        count(lc);
+    } else {
+        const bool vec = c.K % 4 == 0 && a16(c.A, c.lda);
+        p.absmax_out = c.absmax_out;
+        const size_t smem = skinny_n_smem(c.N, c.K);
+        const int grid = grid_for(lc, ((int64_t)c.M + 15) / 16 * 32, kThreads, 4);
+        auto launch = [&](auto kern) -> cudaError_t {
+            if (smem > 48 * 1024) {   // opt in (per device, idempotent; cheap next to a product with K > 700)
+                cudaError_t e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSkinnyNSmemMax);
+                if (e1 != cudaSuccess) return e1;
+            }
+            kern<<<grid, kThreads, smem, lc.stream>>>(A, c.lda, B, c.ldb, p);
+            return cudaSuccess;
+        };
+        cudaError_t e1;
+        const int nj = (c.N + 3) / 4;
+        if (vec) e1 = nj == 1 ? launch(k_skinny_n<4, 4>) : nj == 2 ? launch(k_skinny_n<4, 8>) : nj == 3 ? launch(k_skinny_n<4, 12>) : launch(k_skinny_n<4, 16>);
+        else e1 = nj == 1 ? launch(k_skinny_n<1, 4>) : nj == 2 ? launch(k_skinny_n<1, 8>) : nj == 3 ? launch(k_skinny_n<1, 12>) : launch(k_skinny_n<1, 16>);
+        if (e1 != cudaSuccess) return -(int)e1;
+        count(lc);
+        if (absmax_done) *absmax_done = p.absmax_out != nullptr ? 1 : 0;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
 }  // namespace k
 }  // namespace tops

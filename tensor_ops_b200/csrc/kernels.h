@@ -92,6 +92,9 @@ void loss_vjp(const LaunchCtx&, int loss, const float* A, const float* Y, float*
 
 // ---- CUDA-core GEMM with the same operand/epilogue contract as the tcgen05 engine (fp32 only)
 int gemm_simt(const LaunchCtx&, const GemmCall& c);
+// fp32 products with one dimension <= 16 (streaming CUDA-core kernels): 1 = launched, 0 = not applicable, < 0 = -cudaError
+int gemm_skinny_kind(const GemmCall& c);   // 0 = not applicable
+int gemm_skinny(const LaunchCtx&, const GemmCall& c, int* colsum_fused, int* absmax_done);
 
 }  // namespace k
 }  // namespace tops

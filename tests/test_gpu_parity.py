@@ -184,6 +184,42 @@ def test_mlp_heads_vs_oracle(ctx, acts, loss):
         close(dWs[l], ref[3][l], 1e-5, f"dW{l}"); close(dbs[l], ref[4][l], 1e-5, f"db{l}")
 
 
+@pytest.mark.parametrize("B,hidden,classes", [(1000, 64, 10), (777, 37, 5), (4100, 256, 16), (130, 33, 1), (3, 8, 2), (2500, 300, 13)])
+def test_mlp_output_layer_skinny_products(ctx, B, hidden, classes):
+    """An output layer with <= 16 classes: its three products (forward N <= 16, dW M <= 16, dA K <= 16) take the streaming fp32
+    kernels (aligned float4 and unaligned scalar variants, every count of thin columns); checked against the oracle in every
+    parity mode's tolerance through both heads, and through the bare ffLayer gradient with the same shapes."""
+    rng = np.random.default_rng(B + hidden + classes)
+    f = lambda a: a.astype(np.float32).astype(np.float64)
+    dims = [48, hidden, classes]
+    Ws = [f(rng.normal(0, 1 / np.sqrt(dims[l]), (dims[l + 1], dims[l]))) for l in range(2)]
+    bs = [f(rng.normal(0, 0.5, dims[l + 1])) for l in range(2)]
+    X = f(rng.uniform(0, 1, (B, dims[0])))
+    for acts, loss in ((["logistic", "softmax"], "crossEntropy"), (["logistic", "logistic"], "squaredError")):
+        if classes == 1 and loss == "crossEntropy":
+            continue                          # softmax over one class is the constant 1: every gradient is exactly zero
+        Y = f(np.eye(classes)[rng.integers(0, classes, B)]) if loss == "crossEntropy" else f(rng.uniform(0, 1, (B, classes)))
+        ref = O.mlp_dense_fwd_grad(X, Ws, bs, acts, loss, Y)
+        amap = {"logistic": tb.ACT_LOGISTIC, "softmax": tb.ACT_SOFTMAX}
+        n0 = ctx.launch_count()
+        A, L, dX, dWs, dbs = nn.mlp_fwd_grad([ctx.from_numpy(w) for w in Ws], [ctx.from_numpy(b) for b in bs], [amap[a] for a in acts],
+                                             tb.LOSS_CROSS_ENTROPY if loss == "crossEntropy" else tb.LOSS_SQUARED_ERROR, ctx.from_numpy(X), ctx.from_numpy(Y))
+        assert ctx.launch_count() > n0
+        close(A, ref[0], 1e-5, "A"); close(dX, ref[2], 1e-5, "dX")
+        assert abs(L.unScalar() - ref[1]) <= 1e-5 * abs(ref[1])
+        for l in range(2):
+            close(dWs[l], ref[3][l], 1e-5, f"dW{l}"); close(dbs[l], ref[4][l], 1e-5, f"db{l}")
+    # the same thin shapes through ffLayer' >>> logistic with a supplied cotangent, and a plain product with a thin inner dimension
+    H = f(rng.uniform(0, 1, (B, hidden))); dA = f(rng.normal(size=(B, classes)))
+    ref = O.fflayer_logistic_dense(H, Ws[1], bs[1], dA)
+    got = nn.fflayer_fwd_grad(ctx.from_numpy(H), ctx.from_numpy(Ws[1]), ctx.from_numpy(bs[1]), ctx.from_numpy(dA))
+    for name, t, r in zip(("A", "dX", "dW", "db"), got, ref):
+        close(t, r, 1e-5, f"fflayer {name}")
+    from tensor_ops_b200.tensor import CuTensor
+    close(ctx.from_numpy(dA).gemm(ctx.from_numpy(Ws[1])), dA @ Ws[1], 1e-5, "thin-K product")
+    close(ctx.from_numpy(H).gemm(CuTensor.transp(ctx.from_numpy(Ws[1]))), H @ Ws[1].T, 1e-5, "thin-N product")
+
+
 # ------------------------------------------------------------------------------------------ per-sample TOp algebra on the device
 def test_dots_golden_per_sample_netgrad_and_training(ctx):
     """config 1 plumbing (tensor-ops-dots 2->16->1): netGrad per sample and 200 per-sample SGD steps (Dots.hs:74-80)."""
