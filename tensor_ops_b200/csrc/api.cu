@@ -308,16 +308,12 @@ int run_gemm_f16x3(tops_ctx* ctx, const GemmCall& c0) {
     tops_ctx::SplitEntry a, b;
     TRY(split_operand_f16(ctx, c0.A, a_rows, a_cols, tmp, &a));
     TRY(split_operand_f16(ctx, c0.B, b_rows, b_cols, tmp, &b));
-    int64_t sd[1] = {1};
-    tops_buf* sc = nullptr;
-    TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &sc)); tmp.keep(sc);
-    k::f16x3_pair_scale(lc_of(ctx), a.scale2, b.scale2, (float*)sc->data);
     GemmCall c = c0;
     c.dtype = 2; c.passes = 0;
     c.A = a.hi; c.A2 = a.lo; c.lda = a.ld;
     c.B = b.hi; c.B2 = b.lo; c.ldb = b.ld;
     c.B16 = c.Blo16 = nullptr;
-    c.acc_scale_ptr = (const float*)sc->data;
+    c.acc_scale_ptr = a.scale2 + 1; c.acc_scale_ptr2 = b.scale2 + 1;   // 1 / sA and 1 / sB (powers of two), multiplied in the epilogue
     SplitScope* scope = ctx->split_scope;
     int max_done = 0;
     TRY(want_out_max(ctx, c, &max_done));

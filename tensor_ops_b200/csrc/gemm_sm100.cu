@@ -161,7 +161,7 @@ int gemm_umma_launch(const GemmCall& c, cudaStream_t stream, unsigned int* watch
     // F16X3: k-blocks hold 64 K-elements and 12 MMAs; 2 k-blocks = 128 K-elements = 24 MMAs per chunk.
     p.chunk_kb = c.chunk_kb > 0 ? c.chunk_kb : (c.dtype == 2 ? 2 : 4);
     p.chunk_head_kb = c.chunk_head_kb > p.chunk_kb ? c.chunk_head_kb : p.chunk_kb;
-    p.acc_scale_ptr = c.acc_scale_ptr; p.row_scale = c.row_scale; p.row_scale_inv = c.row_scale_inv;
+    p.acc_scale_ptr = c.acc_scale_ptr; p.acc_scale_ptr2 = c.acc_scale_ptr ? c.acc_scale_ptr2 : nullptr; p.row_scale = c.row_scale; p.row_scale_inv = c.row_scale_inv;
     p.out1_pair = c.out1_pair; p.out1b = c.out1b; p.out1_scale_ptr = c.out1_scale_ptr; p.out1_row_scale = c.out1_row_scale;
     p.epi = c.epi; p.act = c.act; p.alpha = c.alpha; p.beta = c.beta;
     p.out0 = c.out0; p.ld_out0 = c.ld_out0;

@@ -81,6 +81,7 @@ struct GemmParams {
     // Chunked kernels: the register accumulators are multiplied by (*acc_scale_ptr) * row_scale[m] (or / row_scale[m]) before the
     // epilogue math.  F16X3 operands are stored scaled by powers of two; these factors undo the scaling exactly.
     const float* acc_scale_ptr;   // device scalar, NULL = 1
+    const float* acc_scale_ptr2;  // a second device scalar multiplied in (the other operand's inverse scale), NULL = 1
     const float* row_scale;       // [M], NULL = 1
     int row_scale_inv;            // 1: divide by row_scale[m] instead of multiplying
     // out1 written as an fp16 PAIR (staged fp32 epilogues only): t = out1 * (*out1_scale_ptr) * out1_row_scale[m];
@@ -1031,6 +1032,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             {
                 float rs = p.acc_scale_ptr != nullptr ? __ldg(p.acc_scale_ptr) : 1.0f;   // undo the power-of-two operand scaling (exact)
+                if (p.acc_scale_ptr2 != nullptr) rs *= __ldg(p.acc_scale_ptr2);
                 if (p.row_scale != nullptr && row < p.M) {
                     const float r = __ldg(p.row_scale + row);
                     rs *= p.row_scale_inv ? __frcp_rn(r) : r;   // powers of two: exact

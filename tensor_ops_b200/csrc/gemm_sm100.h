@@ -18,6 +18,7 @@ struct GemmCall {
     // dtype 2: the operands were scaled by powers of two when they were split; the accumulators are multiplied by
     // (*acc_scale_ptr) * row_scale[m] (or / row_scale[m]) before the epilogue math (all factors powers of two: exact)
     const float* acc_scale_ptr;           // device scalar, NULL = 1
+    const float* acc_scale_ptr2;          // second device scalar factor (needs acc_scale_ptr), NULL = 1
     const float* row_scale; int row_scale_inv;   // [M] device vector, NULL = 1
     // out1 as an fp16 pair for the next F16X3 GEMM: t = out1 * (*out1_scale_ptr) * out1_row_scale[m]; out1 <- fp16(t), out1b <- fp16(t - fp16(t))
     int out1_pair; void* out1b; const float* out1_scale_ptr; const float* out1_row_scale;
