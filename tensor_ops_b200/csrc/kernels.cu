@@ -1152,11 +1152,16 @@ __device__ __forceinline__ void block_absmax_commit(float amax, unsigned int* ou
 
 // thin operand rows [r0, r0 + nrows) -> sT[row][16] (zero padded), coalesced
 __device__ __forceinline__ void skinny_stage_thin(float (*sT)[16], const float* __restrict__ T, long long ldt, int64_t r0, int nrows, int n) {
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
-    for (int i = tid; i < nrows * 16; i += nthreads) {
-        const int r = i >> 4, j = i & 15;
-        sT[r][j] = j < n ? __ldg(T + (r0 + r) * ldt + j) : 0.f;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    constexpr int PER = kSkinnyRows * 16 / kSkinnyThreads;
+    float tmp[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {                  // all loads in flight before the first store
+        const int i = tid + u * kSkinnyThreads, r = i >> 4, j = i & 15;
+        tmp[u] = (r < nrows && j < n) ? __ldg(T + (r0 + r) * ldt + j) : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { const int i = tid + u * kSkinnyThreads; sT[i >> 4][i & 15] = tmp[u]; }
 }
 template <int VEC> struct SkinnyVec { float v[VEC]; };
 template <int VEC> __device__ __forceinline__ SkinnyVec<VEC> skinny_ld(const float* p) {
@@ -1212,32 +1217,39 @@ __global__ void __launch_bounds__(kSkinnyThreads) k_skinny_k(const float* __rest
         // kSkinnyRows is a multiple of kSkinnyBatch * TY (TY | 16), so the batches of consecutive passes continue the same sequence
         for (int rb = threadIdx.y; rb < nrows; rb += (int)stride) {
             SkinnyVec<VEC> a[kSkinnyBatch];
+            int ridx[kSkinnyBatch]; bool okr[kSkinnyBatch];
 #pragma unroll
-            for (int i = 0; i < kSkinnyBatch; ++i) a[i] = nxt[i];
+            for (int i = 0; i < kSkinnyBatch; ++i) { a[i] = nxt[i]; okr[i] = rb + i * TY < nrows; ridx[i] = okr[i] ? rb + i * TY : rb; }
             fetch(r0 + rb + stride);
+            // the batch's rows are computed together, branch-free (rows past the end repeat row rb and are not stored):
+            // kSkinnyBatch * VEC independent FMA chains instead of VEC
+            float acc[kSkinnyBatch][VEC];
 #pragma unroll
-            for (int i = 0; i < kSkinnyBatch; ++i) {
-                const int r = rb + i * TY;
-                if (r >= nrows) break;
-                float acc[VEC];
+            for (int i = 0; i < kSkinnyBatch; ++i)
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+                for (int v = 0; v < VEC; ++v) acc[i][v] = 0.f;
 #pragma unroll
-                for (int j4 = 0; j4 < NJ / 4; ++j4) {
-                    const float4 t = *reinterpret_cast<const float4*>(&sT[r][j4 * 4]);
+            for (int j4 = 0; j4 < NJ / 4; ++j4) {
+#pragma unroll
+                for (int i = 0; i < kSkinnyBatch; ++i) {
+                    const float4 t = *reinterpret_cast<const float4*>(&sT[ridx[i]][j4 * 4]);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
-                        acc[v] = fmaf(t.x, w[j4 * 4][v], acc[v]); acc[v] = fmaf(t.y, w[j4 * 4 + 1][v], acc[v]);
-                        acc[v] = fmaf(t.z, w[j4 * 4 + 2][v], acc[v]); acc[v] = fmaf(t.w, w[j4 * 4 + 3][v], acc[v]);
+                        acc[i][v] = fmaf(t.x, w[j4 * 4][v], acc[i][v]); acc[i][v] = fmaf(t.y, w[j4 * 4 + 1][v], acc[i][v]);
+                        acc[i][v] = fmaf(t.z, w[j4 * 4 + 2][v], acc[i][v]); acc[i][v] = fmaf(t.w, w[j4 * 4 + 3][v], acc[i][v]);
                     }
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < kSkinnyBatch; ++i) {
+                if (!okr[i]) continue;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    if constexpr (LOGI) acc[v] *= a[i].v[v] * (1.0f - a[i].v[v]);
-                    else acc[v] = dact ? acc[v] * act_deriv_from_out(p.act, a[i].v[v]) : acc[v] * p.alpha;
-                    csum[v] += acc[v]; amax = fmaxf(amax, fabsf(acc[v]));
+                    if constexpr (LOGI) acc[i][v] *= a[i].v[v] * (1.0f - a[i].v[v]);
+                    else acc[i][v] = dact ? acc[i][v] * act_deriv_from_out(p.act, a[i].v[v]) : acc[i][v] * p.alpha;
+                    csum[v] += acc[i][v]; amax = fmaxf(amax, fabsf(acc[i][v]));
                 }
-                skinny_st<VEC>(out + (r0 + r) * p.ld_out0 + f0, acc);
+                skinny_st<VEC>(out + (r0 + ridx[i]) * p.ld_out0 + f0, acc[i]);
             }
         }
     }
@@ -1289,16 +1301,20 @@ __global__ void __launch_bounds__(kSkinnyThreads) k_skinny_m(const float* __rest
         if (!col_ok) continue;
         for (int rb = threadIdx.y; rb < nrows; rb += (int)stride) {
             SkinnyVec<VEC> x[kSkinnyBatch];
-#pragma unroll
-            for (int i = 0; i < kSkinnyBatch; ++i) x[i] = nxt[i];
-            fetch(r0 + rb + stride);
+            int ridx[kSkinnyBatch];
 #pragma unroll
             for (int i = 0; i < kSkinnyBatch; ++i) {
-                const int r = rb + i * TY;
-                if (r >= nrows) break;
+                const bool okr = rb + i * TY < nrows;
+                ridx[i] = okr ? rb + i * TY : rb;
 #pragma unroll
-                for (int j4 = 0; j4 < NJ / 4; ++j4) {
-                    const float4 t = *reinterpret_cast<const float4*>(&sT[r][j4 * 4]);
+                for (int v = 0; v < VEC; ++v) x[i].v[v] = okr ? nxt[i].v[v] : 0.f;   // rows past the end contribute nothing
+            }
+            fetch(r0 + rb + stride);
+#pragma unroll
+            for (int j4 = 0; j4 < NJ / 4; ++j4) {
+#pragma unroll
+                for (int i = 0; i < kSkinnyBatch; ++i) {
+                    const float4 t = *reinterpret_cast<const float4*>(&sT[ridx[i]][j4 * 4]);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         acc[j4 * 4][v] = fmaf(t.x, x[i].v[v], acc[j4 * 4][v]); acc[j4 * 4 + 1][v] = fmaf(t.y, x[i].v[v], acc[j4 * 4 + 1][v]);
@@ -1350,7 +1366,7 @@ template <int H, int BIT> __device__ __forceinline__ void skinny_halve(float (&a
 // segments and the matching pieces of W (shared memory, 128 contiguous bytes broadcast to the four quarters) serve four rows per
 // read.  The 8 partial sums of a row meet in a halving exchange (14 shuffles per 16 columns); lane kl ends with columns 2kl, 2kl+1.
 template <int VEC, int NJ>
-__global__ void __launch_bounds__(256) k_skinny_n(const float* __restrict__ X, long long ldx, const float* __restrict__ W, long long ldw, GemmParams p) {
+__global__ void __launch_bounds__(256, 2) k_skinny_n(const float* __restrict__ X, long long ldx, const float* __restrict__ W, long long ldw, GemmParams p) {
     extern __shared__ __align__(16) float sW[];
     const int ldk = (p.K + 3) / 4 * 4 + 4;
     for (int j = 0; j < NJ; ++j)                                     // rows N..NJ-1 are zero: the inner loops run over all NJ
@@ -1374,14 +1390,18 @@ __global__ void __launch_bounds__(256) k_skinny_n(const float* __restrict__ X, l
         const float* xrow[R];
         bool ok[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { const int64_t row = s0 + q + 4 * r; ok[r] = row < p.M; xrow[r] = X + (ok[r] ? row : 0) * ldx + kl * VEC; }
-#pragma unroll 2
-        for (int k0 = 0; k0 < p.K; k0 += CH) {
-            const bool kin = k0 + kl * VEC < p.K;
+        for (int r = 0; r < R; ++r) {   // rows past the end re-read the last row (never stored): the loads need no predicate
+            const int64_t row = s0 + q + 4 * r;
+            ok[r] = row < p.M;
+            xrow[r] = X + (ok[r] ? row : (int64_t)p.M - 1) * ldx + kl * VEC;
+        }
+        auto chunk = [&](int k0, auto tail_tag) {
+            constexpr bool TAIL = decltype(tail_tag)::value;
+            const bool kin = !TAIL || k0 + kl * VEC < p.K;
             SkinnyVec<VEC> x[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                if (ok[r] && kin) x[r] = skinny_ld<VEC>(xrow[r] + k0);
+                if (kin) x[r] = skinny_ld<VEC>(xrow[r] + k0);
                 else {
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) x[r].v[v] = 0.f;
@@ -1391,7 +1411,7 @@ __global__ void __launch_bounds__(256) k_skinny_n(const float* __restrict__ X, l
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 float wv[VEC];
-                if constexpr (VEC == 4) {   // (the last chunk of a K that is not a multiple of 32 ends inside the row: lanes beyond it read nothing)
+                if constexpr (VEC == 4) {   // (a tail chunk ends inside the row: lanes beyond it read nothing)
                     const float4 t = kin ? *reinterpret_cast<const float4*>(wp + j * ldk) : make_float4(0.f, 0.f, 0.f, 0.f);
                     wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
                 } else wv[0] = kin ? wp[j * ldk] : 0.f;
@@ -1400,7 +1420,11 @@ __global__ void __launch_bounds__(256) k_skinny_n(const float* __restrict__ X, l
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) acc[r][j] = fmaf(x[r].v[v], wv[v], acc[r][j]);
             }
-        }
+        };
+        const int k_main = p.K / CH * CH;
+#pragma unroll 2
+        for (int k0 = 0; k0 < k_main; k0 += CH) chunk(k0, std::false_type{});
+        if (k_main < p.K) chunk(k_main, std::true_type{});
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             skinny_halve<8, 4>(acc[r], lane); skinny_halve<4, 2>(acc[r], lane); skinny_halve<2, 1>(acc[r], lane);
