@@ -1017,7 +1017,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     ptx::tmem_ld_wait();
                     if (c + 1 < HC / 16) ptx::tmem_ld_32x32b_x16(t_row + (c + 1) * 16, raw[(c + 1) & 1]);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) sum[c * 16 + e] += __uint_as_float(raw[c & 1][e]);   // fp32 add, round to nearest
+                    for (int e = 0; e < 16; e += 2) ptx::add2(sum[c * 16 + e], sum[c * 16 + e + 1], raw[c & 1][e], raw[c & 1][e + 1]);   // fp32 adds, round to nearest, two per instruction
                 }
                 ptx::tcgen05_fence_before();
                 __syncwarp();
@@ -1049,12 +1049,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int g = 0; g < HC / 4; ++g) {
                         const float4 b4 = __ldg(b4p + g);
-                        sum[g * 4] = fmaf(sum[g * 4], rs, b4.x); sum[g * 4 + 1] = fmaf(sum[g * 4 + 1], rs, b4.y);
-                        sum[g * 4 + 2] = fmaf(sum[g * 4 + 2], rs, b4.z); sum[g * 4 + 3] = fmaf(sum[g * 4 + 3], rs, b4.w);
+                        ptx::fma2(sum[g * 4], sum[g * 4 + 1], rs, b4.x, b4.y);
+                        ptx::fma2(sum[g * 4 + 2], sum[g * 4 + 3], rs, b4.z, b4.w);
                     }
                 } else if (p.acc_scale_ptr != nullptr || p.row_scale != nullptr) {
 #pragma unroll
-                    for (int e = 0; e < HC; ++e) sum[e] *= rs;
+                    for (int e = 0; e < HC; e += 2) ptx::mul2(sum[e], sum[e + 1], rs);
                 }
             }
             if (p.out1_pair) {

@@ -296,5 +296,26 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Packed fp32 pairs (sm_100: FADD2 / FFMA2 / FMUL2): two IEEE round-to-nearest operations per issued instruction — the epilogue
+// warps are latency-bound (2 warps per scheduler), so halving the instruction count of their long elementwise stretches is time.
+__device__ __forceinline__ void add2(float& a0, float& a1, uint32_t b0, uint32_t b1) {
+    asm("{ .reg .b64 ra, rb; mov.b64 ra, {%0,%1}; mov.b64 rb, {%2,%3}; add.rn.f32x2 ra, ra, rb; mov.b64 {%0,%1}, ra; }" : "+f"(a0), "+f"(a1) : "r"(b0), "r"(b1));
+}
+// (a0, a1) = (a0, a1) * (m, m) + (c0, c1)
+__device__ __forceinline__ void fma2(float& a0, float& a1, float m, float c0, float c1) {
+    asm("{ .reg .b64 ra, rm, rc; mov.b64 ra, {%0,%1}; mov.b64 rm, {%2,%2}; mov.b64 rc, {%3,%4}; fma.rn.f32x2 ra, ra, rm, rc; mov.b64 {%0,%1}, ra; }"
+        : "+f"(a0), "+f"(a1) : "f"(m), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void mul2(float& a0, float& a1, float m) {
+    asm("{ .reg .b64 ra, rm; mov.b64 ra, {%0,%1}; mov.b64 rm, {%2,%2}; mul.rn.f32x2 ra, ra, rm; mov.b64 {%0,%1}, ra; }" : "+f"(a0), "+f"(a1) : "f"(m));
+}
+// the same on values kept packed in a 64-bit register pair
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 }  // namespace ptx
 }  // namespace tops
