@@ -17,12 +17,17 @@ PEAK_HBM = 6546.2
 
 
 def timeit(fn, steps=10, warm=3):
+    """(ms per step over `steps` back-to-back calls with one synchronise at the end, per-kernel device ms from a second, profiled pass —
+    the profiling events sit between the launches and would otherwise be part of the step time)"""
     for _ in range(warm): fn()
-    ctx.sync(); ctx.profile(True)
+    ctx.sync()
     t0 = time.perf_counter()
     for _ in range(steps): fn()
-    prof = ctx.profile_summary(); ctx.profile(False)     # synchronises
+    ctx.sync()
     wall = (time.perf_counter() - t0) / steps * 1e3
+    ctx.profile(True)
+    for _ in range(steps): fn()
+    prof = ctx.profile_summary(); ctx.profile(False)     # synchronises
     return wall, {k: v["ms"] / v["launches"] * (v["launches"] / steps) for k, v in prof.items()}
 
 
@@ -42,7 +47,7 @@ if "3" in which:
     acts = [L.ACT_LOGISTIC, L.ACT_LOGISTIC, L.ACT_SOFTMAX]
     for prec, name in precs(("f16x3", "tf32bf16", "tf32x3", "tf32")):
         ctx.set_precision(prec)
-        ms, per = timeit(lambda: nn.mlp_fwd_grad(Ws, bs, acts, L.LOSS_CROSS_ENTROPY, X, Y))
+        ms, per = timeit(lambda: nn.mlp_fwd_grad(Ws, bs, acts, L.LOSS_CROSS_ENTROPY, X, Y), steps=30)
         flop = 6.0 * B * (784 * 512 + 512 * 256 + 256 * 10)
         with ctx.record(arena_bytes=3 << 30) as g:     # the whole netGrad recorded once, replayed as one graph launch
             nn.mlp_fwd_grad(Ws, bs, acts, L.LOSS_CROSS_ENTROPY, X, Y)
