@@ -561,6 +561,47 @@ __global__ void k_softmax_ce_small(const float* __restrict__ Z, const float* __r
         else if (colsum != nullptr && threadIdx.x < cols) atomicAdd(colsum + threadIdx.x, t);
     }
 }
+// softmax map / its VJP on rows of <= CMAX columns: one thread per row (see k_softmax_ce_small), 16-byte accesses when cols % 4 == 0
+template <int CMAX, int MODE>   // MODE 0: out = softmax(Z);  MODE 1: out = VJP of softmax at Z applied to dA
+__global__ void k_softmax_small(const float* __restrict__ Z, const float* __restrict__ dA, float* __restrict__ out, int64_t rows, int cols, int vec) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        float e[CMAX], d[CMAX];
+        const float* z = Z + r * cols;
+        const float* da = MODE == 1 ? dA + r * cols : nullptr;
+        if (vec) {
+#pragma unroll
+            for (int c4 = 0; c4 < CMAX / 4; ++c4) {
+                if (c4 * 4 < cols) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(z) + c4);
+                    e[c4 * 4] = t.x; e[c4 * 4 + 1] = t.y; e[c4 * 4 + 2] = t.z; e[c4 * 4 + 3] = t.w;
+                    if (MODE == 1) { const float4 u = __ldg(reinterpret_cast<const float4*>(da) + c4); d[c4 * 4] = u.x; d[c4 * 4 + 1] = u.y; d[c4 * 4 + 2] = u.z; d[c4 * 4 + 3] = u.w; }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) if (c < cols) { e[c] = __ldg(z + c); if (MODE == 1) d[c] = __ldg(da + c); }
+        }
+        float se = 0.f, s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            e[c] = c < cols ? __expf(e[c]) : 0.f;          // map exp (no max-subtraction: NeuralNet.hs:52-59)
+            se += e[c];
+            if (MODE == 1) s += c < cols ? d[c] * e[c] : 0.f;
+        }
+        const float rinv = 1.0f / se, ds = -(rinv * rinv) * s;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) e[c] = MODE == 0 ? e[c] * rinv : (c < cols ? (ds + d[c] * rinv) * e[c] : 0.f);
+        float* o = out + r * cols;
+        if (vec) {
+#pragma unroll
+            for (int c4 = 0; c4 < CMAX / 4; ++c4)
+                if (c4 * 4 < cols) reinterpret_cast<float4*>(o)[c4] = make_float4(e[c4 * 4], e[c4 * 4 + 1], e[c4 * 4 + 2], e[c4 * 4 + 3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) if (c < cols) o[c] = e[c];
+        }
+    }
+}
 __global__ void k_loss_vjp(int loss, const float* __restrict__ A, const float* __restrict__ Y, float* __restrict__ dA, float* __restrict__ out, int64_t n) {
     __shared__ float sh[32];
     float acc = 0.f;
@@ -1080,10 +1121,20 @@ void diag_extract(const LaunchCtx& lc, const float* a, float* out, int64_t n, in
 
 void softmax_rows(const LaunchCtx& lc, const float* Z, float* A, int64_t rows, int64_t cols) {
     if (rows * cols <= 0) return;
+    if (cols <= 16) {
+        const int vec = cols % 4 == 0 && aligned16(Z) && aligned16(A);
+        k_softmax_small<16, 0><<<grid_for(lc, rows), kThreads, 0, lc.stream>>>(Z, nullptr, A, rows, (int)cols, vec); count(lc);
+        return;
+    }
     k_softmax_rows<0><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, nullptr, A, nullptr, nullptr, rows, cols, nullptr); count(lc);
 }
 void softmax_vjp_rows(const LaunchCtx& lc, const float* Z, const float* dA, float* dZ, int64_t rows, int64_t cols) {
     if (rows * cols <= 0) return;
+    if (cols <= 16) {
+        const int vec = cols % 4 == 0 && aligned16(Z) && aligned16(dA) && aligned16(dZ);
+        k_softmax_small<16, 1><<<grid_for(lc, rows), kThreads, 0, lc.stream>>>(Z, dA, dZ, rows, (int)cols, vec); count(lc);
+        return;
+    }
     k_softmax_rows<1><<<grid_for(lc, rows * 32), kThreads, 0, lc.stream>>>(Z, dA, nullptr, dZ, nullptr, rows, cols, nullptr); count(lc);
 }
 bool softmax_ce_rows(const LaunchCtx& lc, const float* Z, const float* Y, float* A, float* dZ, float* loss, int64_t rows, int64_t cols, float* db) {

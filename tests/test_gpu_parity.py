@@ -195,8 +195,8 @@ def test_mlp_output_layer_skinny_products(ctx, B, hidden, classes):
     Ws = [f(rng.normal(0, 1 / np.sqrt(dims[l]), (dims[l + 1], dims[l]))) for l in range(2)]
     bs = [f(rng.normal(0, 0.5, dims[l + 1])) for l in range(2)]
     X = f(rng.uniform(0, 1, (B, dims[0])))
-    for acts, loss in ((["logistic", "softmax"], "crossEntropy"), (["logistic", "logistic"], "squaredError")):
-        if classes == 1 and loss == "crossEntropy":
+    for acts, loss in ((["logistic", "softmax"], "crossEntropy"), (["logistic", "logistic"], "squaredError"), (["logistic", "softmax"], "squaredError")):
+        if classes == 1 and acts[-1] == "softmax":
             continue                          # softmax over one class is the constant 1: every gradient is exactly zero
         Y = f(np.eye(classes)[rng.integers(0, classes, B)]) if loss == "crossEntropy" else f(rng.uniform(0, 1, (B, classes)))
         ref = O.mlp_dense_fwd_grad(X, Ws, bs, acts, loss, Y)
@@ -218,6 +218,24 @@ def test_mlp_output_layer_skinny_products(ctx, B, hidden, classes):
     from tensor_ops_b200.tensor import CuTensor
     close(ctx.from_numpy(dA).gemm(ctx.from_numpy(Ws[1])), dA @ Ws[1], 1e-5, "thin-K product")
     close(ctx.from_numpy(H).gemm(CuTensor.transp(ctx.from_numpy(Ws[1]))), H @ Ws[1].T, 1e-5, "thin-N product")
+
+
+@pytest.mark.parametrize("classes", [20, 32, 40])
+def test_softmax_ce_head_wider_than_the_thread_per_row_kernel(ctx, classes):
+    """17..32 classes: warp-per-row head with db fused by lane; more than 32: the head leaves db to the column-sum pass."""
+    rng = np.random.default_rng(classes)
+    f = lambda a: a.astype(np.float32).astype(np.float64)
+    dims, B = [30, 24, classes], 515
+    Ws = [f(rng.normal(0, 1 / np.sqrt(dims[l]), (dims[l + 1], dims[l]))) for l in range(2)]
+    bs = [f(rng.normal(0, 0.5, dims[l + 1])) for l in range(2)]
+    X = f(rng.uniform(0, 1, (B, dims[0]))); Y = f(np.eye(classes)[rng.integers(0, classes, B)])
+    ref = O.mlp_dense_fwd_grad(X, Ws, bs, ["logistic", "softmax"], "crossEntropy", Y)
+    A, L, dX, dWs, dbs = nn.mlp_fwd_grad([ctx.from_numpy(w) for w in Ws], [ctx.from_numpy(b) for b in bs], [tb.ACT_LOGISTIC, tb.ACT_SOFTMAX],
+                                         tb.LOSS_CROSS_ENTROPY, ctx.from_numpy(X), ctx.from_numpy(Y))
+    close(A, ref[0], 1e-5, "A"); close(dX, ref[2], 1e-5, "dX")
+    assert abs(L.unScalar() - ref[1]) <= 1e-5 * abs(ref[1])
+    for l in range(2):
+        close(dWs[l], ref[3][l], 1e-5, f"dW{l}"); close(dbs[l], ref[4][l], 1e-5, f"db{l}")
 
 
 # ------------------------------------------------------------------------------------------ per-sample TOp algebra on the device
@@ -386,6 +404,9 @@ def test_softmax_reference_form(ctx):
     z = rng.normal(size=(40, 10)); e = np.exp(z)
     zt = ctx.from_numpy(z)   # keep the handle alive: `.b` of a temporary would be released before the call
     close(zt._new(tb._lib.lib.tops_map_rows_softmax, zt.b), e / e.sum(1, keepdims=True), 1e-6, "softmax rows")
+    for rows, cols in ((1000, 3), (517, 12), (4096, 16), (300, 20), (64, 100)):   # thread-per-row (scalar / 16-byte) and warp-per-row kernels
+        z = rng.normal(size=(rows, cols)); e = np.exp(z); zt = ctx.from_numpy(z)
+        close(zt._new(tb._lib.lib.tops_map_rows_softmax, zt.b), e / e.sum(1, keepdims=True), 1e-6, f"softmax rows {rows}x{cols}")
     # the reference softmax TOp on one sample, through the generic algebra
     v = rng.normal(size=10)
     close(TO.runTOp(nn.softmax(), [ctx.from_numpy(v)])[0], np.exp(v) / np.exp(v).sum(), 1e-6, "softmax TOp")
