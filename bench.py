@@ -492,6 +492,11 @@ def main():
                               best, f"tops_fflayer_step_dp: NCCL all-reduce of [dW||db] on a communication stream, started when dW/db are complete, overlapped with the dX GEMM ({best.split('-')[1]} SMs left free)")
         allreduce_kind += " — fastest of the candidates verified and timed on this run (allreduce_trial)"
 
+    if world > 1:
+        # the schedule trials above are ~60 back-to-back steps of preparation, not part of the benchmark: let the boards' power
+        # management settle before the warm-up (multi-GPU boxes report sw_power_cap right after such a burst)
+        torch.cuda.synchronize()
+        time.sleep(1.0)
     for _ in range(args.warmup):
         step()
     barrier()
