@@ -32,6 +32,7 @@ struct tops_ctx {
     // init, so it drains every 2 k-blocks (6e-7); the gradient GEMMs every 4 (1.1e-6, 7 % faster).  TOPS_F16X3_CHUNK / _FWD_CHUNK override.
     int f16x3_chunk_kb = 4;
     int f16x3_fwd_chunk_kb = 2;
+    bool skinny = true;           // products with a dimension <= 16 take the streaming fp32 kernels; TOPS_SKINNY=0: they stay on the tcgen05 path (padded fp16 planes)
     int f16x3_fwd_head_kb = 4;    // first two chunks of every tile of the fused forward GEMM (lookahead for its epilogue); TOPS_F16X3_FWD_HEAD
     struct SplitEntry { const void* src; int64_t rows, cols; void* hi; void* lo; long long ld; float* scale2; };
     struct SplitScope* split_scope = nullptr;   // fp16 pairs already made inside the current API call
@@ -331,7 +332,7 @@ int run_gemm(tops_ctx* ctx, GemmCall c) {
     if (c.M <= 0 || c.N <= 0) return TOPS_OK;
     // One tiny dimension (an MLP's output layer): streaming fp32 CUDA-core kernels — HBM-bound work the tensor-core tiles and the
     // operand splits would only slow down.  FP32_SIMT keeps its single reference kernel.
-    if (ctx->precision != TOPS_PREC_FP32_SIMT && k::gemm_skinny_kind(c) != 0) {
+    if (ctx->skinny && ctx->precision != TOPS_PREC_FP32_SIMT && k::gemm_skinny_kind(c) != 0) {
         ProfScope prof_(ctx, c.tag ? c.tag : "gemm", 2.0 * c.M * c.N * (double)c.K,
                         4.0 * ((double)c.M * c.K + (double)c.N * c.K + (double)c.M * c.N * ((c.aux0 ? 1 : 0) + 1)));
         if (c.epi == EPI_ATOMIC && !c.accumulate) CUDA_TRY(ctx, cudaMemsetAsync(c.out0, 0, sizeof(float) * (size_t)c.M * (size_t)c.ld_out0, ctx->stream));
@@ -432,6 +433,7 @@ extern "C" int tops_init(int device, tops_ctx** out) {
     memset(ctx->wd_host, 0, 64);
     if (const char* e = getenv("TOPS_F16X3_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->f16x3_chunk_kb = v; }
     if (const char* e = getenv("TOPS_F16X3_FWD_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->f16x3_fwd_chunk_kb = v; }
+    if (const char* e = getenv("TOPS_SKINNY")) ctx->skinny = atoi(e) != 0;
     if (const char* e = getenv("TOPS_F16X3_FWD_HEAD")) { const int v = atoi(e); if (v >= 0 && v <= 64) ctx->f16x3_fwd_head_kb = v; }
     *out = ctx;
     return TOPS_OK;
@@ -941,7 +943,7 @@ extern "C" int tops_gmul_sum_rows_vjp(tops_ctx* ctx, int lM, int lO, int lN, con
         TRY(prep_out(ctx, dx, TOPS_F32, x->rank, x->dims));
         TRY(prep_out(ctx, dy, TOPS_F32, y->rank, y->dims));
         ProfScope prof_(ctx, "gmul_sum_rows_vjp", 4.0 * R * K * N, 4.0 * (2.0 * x->numel + 2.0 * y->numel + R * N));
-        CUDA_TRY(ctx, cudaMemsetAsync((*dy)->data, 0, sizeof(float) * (size_t)(K * N), ctx->stream));
+        if (k::gsr_vjp_needs_zeroed_dy(R, (int)K, (int)N)) CUDA_TRY(ctx, cudaMemsetAsync((*dy)->data, 0, sizeof(float) * (size_t)(K * N), ctx->stream));
         k::gsr_vjp(lc_of(ctx), (const float*)x->data, (const float*)y->data, (const float*)ct->data, (float*)(*dx)->data, (float*)(*dy)->data, A, R, (int)K, (int)N);
         return check_launch(ctx, "gmul_sum_rows_vjp");
     }

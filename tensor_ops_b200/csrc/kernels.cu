@@ -743,6 +743,75 @@ __global__ void __launch_bounds__(kGsrThreads) k_gsr_fwd(const float* __restrict
     }
 }
 
+// The same with y staged in shared memory (K*N floats) by loads that are in flight together with the loads of x — one memory latency
+// instead of one per k of the final contraction — and the contraction spread over all threads (N columns x threads/N slices of k).
+constexpr int kGsrYB = 8;   // y elements per thread whose loads are issued before the x loads (config 5: all of them)
+__global__ void __launch_bounds__(kGsrThreads) k_gsr_fwd_staged(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                                                int64_t A, int64_t R, int K, int N) {
+    extern __shared__ float sh[];
+    const int KT = K < kGsrThreads ? K : kGsrThreads;
+    const int groups = kGsrThreads / KT;
+    const int G3 = N < kGsrThreads ? kGsrThreads / N : 1;   // k slices of the contraction
+    float* ys = sh;                                          // [K][N]
+    float* xp = ys + (size_t)K * N;                          // [groups][K] -> xs[K]
+    float* red = xp + (size_t)groups * K;                    // [G3][N]
+    const int r = blockIdx.x, t = threadIdx.x;
+    const int g = t / KT, kk = t % KT;
+    float yv[kGsrYB];
+#pragma unroll
+    for (int j = 0; j < kGsrYB; ++j) { const int i = t + j * kGsrThreads; yv[j] = i < K * N ? __ldg(y + i) : 0.f; }
+    for (int k0 = 0; k0 < K; k0 += KT) {
+        const int k = k0 + kk;
+        float acc = 0.f;
+        if (g < groups && k < K) {
+            const float* p = x + ((int64_t)g * R + r) * K + k;
+            const int64_t step = (int64_t)groups * R * K;
+            int64_t a = g;
+            for (; a + 7 * groups < A; a += 8 * groups, p += 8 * step) {
+                const float v0 = __ldg(p), v1 = __ldg(p + step), v2 = __ldg(p + 2 * step), v3 = __ldg(p + 3 * step);
+                const float v4 = __ldg(p + 4 * step), v5 = __ldg(p + 5 * step), v6 = __ldg(p + 6 * step), v7 = __ldg(p + 7 * step);
+                acc += ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+            }
+            for (; a < A; a += groups, p += step) acc += __ldg(p);
+            xp[g * K + k] = acc;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kGsrYB; ++j) { const int i = t + j * kGsrThreads; if (i < K * N) ys[i] = yv[j]; }
+    for (int i = t + kGsrYB * kGsrThreads; i < K * N; i += kGsrThreads) ys[i] = __ldg(y + i);
+    __syncthreads();
+    for (int k = t; k < K; k += kGsrThreads) {
+        float s_ = xp[k];
+        for (int gg = 1; gg < groups; ++gg) s_ += xp[gg * K + k];
+        xp[k] = s_;
+    }
+    __syncthreads();
+    if (N < kGsrThreads) {
+        const int n = t % N, kg = t / N;
+        if (kg < G3) {
+            float acc = 0.f;
+            for (int k = kg; k < K; k += G3) acc = fmaf(xp[k], ys[k * N + n], acc);
+            red[kg * N + n] = acc;
+        }
+        __syncthreads();
+        if (t < N) {
+            float acc = red[t];
+            for (int q = 1; q < G3; ++q) acc += red[q * N + t];
+            out[(int64_t)r * N + t] = acc;
+        }
+    } else {
+        for (int n = t; n < N; n += kGsrThreads) {
+            float acc = 0.f;
+            for (int k = 0; k < K; ++k) acc = fmaf(xp[k], ys[k * N + n], acc);
+            out[(int64_t)r * N + n] = acc;
+        }
+    }
+}
+size_t gsr_fwd_staged_smem(int K, int N) {
+    const int KT = K < kGsrThreads ? K : kGsrThreads;
+    return sizeof(float) * ((size_t)K * N + (size_t)(kGsrThreads / KT) * K + (size_t)(N < kGsrThreads ? kGsrThreads / N : 1) * N);
+}
+
 // VJP with cotangent ct[R,N]:  dx[a,r,k] = sum_n ct[r,n] y[k,n]  (the same for every a: written A times, never materialising the
 // broadcast cotangent),  dy[k,n] += (sum_a x[a,r,k]) ct[r,n]  (rank-1 update per r, fp32 reds into the pre-zeroed dy).
 template <int PER>   // PER > 0: dy partials of RB rows kept in PER registers per thread (K*N <= PER * threads); 0: one red per row and entry
@@ -754,7 +823,10 @@ __global__ void __launch_bounds__(kGsrThreads) k_gsr_vjp(const float* __restrict
     float* tk = cts + N;                          // [K]   t[k] = sum_n ct[r,n] y[k,n]
     float* xs = tk + K;                           // [groups][K] -> xs[K]
     const int t = threadIdx.x;
-    for (int i = t; i < K * N; i += kGsrThreads) ys[(i / N) * (N + 1) + (i % N)] = __ldg(y + i);
+    float yv[kGsrYB];                             // the first kGsrYB * threads elements of y: in flight together with the first row's x loads
+#pragma unroll
+    for (int j = 0; j < kGsrYB; ++j) { const int i = t + j * kGsrThreads; yv[j] = i < K * N ? __ldg(y + i) : 0.f; }
+    bool y_staged = false;
     const int KT = K < kGsrThreads ? K : kGsrThreads;
     const int groups = kGsrThreads / KT;
     const int g = t / KT, kk = t % KT;
@@ -763,7 +835,7 @@ __global__ void __launch_bounds__(kGsrThreads) k_gsr_vjp(const float* __restrict
     for (int j = 0; j < (PER > 0 ? PER : 1); ++j) part[j] = 0.f;
     const int64_t r_end = min(R, (int64_t)(blockIdx.x + 1) * RB);
     for (int64_t r = (int64_t)blockIdx.x * RB; r < r_end; ++r) {
-        __syncthreads();                          // previous row's xs / cts / tk fully consumed (and ys loaded, first time)
+        __syncthreads();                          // previous row's xs / cts / tk fully consumed
         for (int n = t; n < N; n += kGsrThreads) cts[n] = __ldg(ct + r * N + n);
         for (int k0 = 0; k0 < K; k0 += KT) {      // row sums of x over a (needed by dy), coalesced along k
             const int k = k0 + kk;
@@ -780,6 +852,12 @@ __global__ void __launch_bounds__(kGsrThreads) k_gsr_vjp(const float* __restrict
                 for (; a < A; a += groups, p += step) acc += __ldg(p);
                 xs[g * K + k] = acc;
             }
+        }
+        if (!y_staged) {
+#pragma unroll
+            for (int j = 0; j < kGsrYB; ++j) { const int i = t + j * kGsrThreads; if (i < K * N) ys[(i / N) * (N + 1) + (i % N)] = yv[j]; }
+            for (int i = t + kGsrYB * kGsrThreads; i < K * N; i += kGsrThreads) ys[(i / N) * (N + 1) + (i % N)] = __ldg(y + i);
+            y_staged = true;
         }
         __syncthreads();
         for (int k = t; k < K; k += kGsrThreads) {
@@ -817,6 +895,107 @@ __global__ void __launch_bounds__(kGsrThreads) k_gsr_vjp(const float* __restrict
     }
 }
 
+// The same VJP without reds and without a zeroed dy: block b does two independent jobs —
+//   (b < R)  dx[:, b, :] = t[k] = sum_n ct[b,n] y[k,n]              (as above)
+//   (b < K)  dy[b, :]    = sum_r (sum_a x[a,r,b]) ct[r,:]            (column b of the row sums, read with stride K: 32-byte sectors from
+//                                                                   L2, where the forward kernel has just left x)
+// so every element of dy is written once, deterministically, and the memset node and the tail of 64-way contended reds disappear
+// (config 5 as a recorded step: 12.3 -> see profiles).  All global loads of a block are issued before its first barrier.
+__global__ void __launch_bounds__(kGsrThreads) k_gsr_vjp_det(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ ct,
+                                                             float* __restrict__ dx, float* __restrict__ dy, int64_t A, int64_t R, int K, int N) {
+    extern __shared__ float sh[];
+    const int G = N < kGsrThreads ? kGsrThreads / N : 1;   // slices (of r, of n) that share a column in the two contractions
+    const int RT = (int)(R < kGsrThreads ? R : kGsrThreads), GA = kGsrThreads / RT;    // job 2: RT threads along r, GA groups along a
+    float* ys = sh;                                   // [K][N+1]
+    float* cts = ys + (size_t)K * (N + 1);            // [N]      ct[b,:]
+    float* tk = cts + N;                              // [K]
+    float* ctall = tk + K;                            // [R][N]
+    float* xpart = ctall + (size_t)R * N;             // [GA][R] -> xs[R]
+    float* red = xpart + (size_t)GA * R;              // [G][N]
+    const int b = blockIdx.x, t = threadIdx.x;
+    const bool job1 = b < R, job2 = b < K;
+    // ---- loads (job 2's strided column of x first: the longest chain)
+    if (job2) {
+        const int rr = t % RT, ga = t / RT;
+        for (int64_t r0 = 0; r0 < R; r0 += RT) {
+            const int64_t r = r0 + rr;
+            float acc = 0.f;
+            if (ga < GA && r < R) {
+                const float* p = x + ((int64_t)ga * R + r) * K + b;
+                const int64_t step = (int64_t)GA * R * K;
+                int64_t a = ga;
+                for (; a + 7 * GA < A; a += 8 * GA, p += 8 * step) {
+                    const float v0 = __ldg(p), v1 = __ldg(p + step), v2 = __ldg(p + 2 * step), v3 = __ldg(p + 3 * step);
+                    const float v4 = __ldg(p + 4 * step), v5 = __ldg(p + 5 * step), v6 = __ldg(p + 6 * step), v7 = __ldg(p + 7 * step);
+                    acc += ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+                }
+                for (; a < A; a += GA, p += step) acc += __ldg(p);
+                xpart[ga * R + r] = acc;
+            }
+        }
+        for (int64_t i = t; i < R * N; i += kGsrThreads) ctall[i] = __ldg(ct + i);
+    }
+    if (job1) {
+        for (int i = t; i < K * N; i += kGsrThreads) ys[(i / N) * (N + 1) + (i % N)] = __ldg(y + i);
+        for (int n = t; n < N; n += kGsrThreads) cts[n] = __ldg(ct + (int64_t)b * N + n);
+    }
+    __syncthreads();
+    // ---- job 1: t[k], then dx
+    if (job1) {
+        for (int k = t; k < K; k += kGsrThreads) {
+            float acc = 0.f;
+            for (int n = 0; n < N; ++n) acc = fmaf(cts[n], ys[k * (N + 1) + n], acc);
+            tk[k] = acc;
+        }
+    }
+    // ---- job 2: xs[r] = sum over the a-groups
+    if (job2) {
+        for (int r = t; r < R; r += kGsrThreads) {
+            float s_ = xpart[r];
+            for (int g = 1; g < GA; ++g) s_ += xpart[g * R + r];
+            xpart[r] = s_;
+        }
+    }
+    __syncthreads();
+    if (job1) {
+        const int KT = K < kGsrThreads ? K : kGsrThreads, groups = kGsrThreads / KT;
+        const int g = t / KT, kk = t % KT;
+        for (int k0 = 0; k0 < K; k0 += KT) {
+            const int k = k0 + kk;
+            if (g < groups && k < K) {
+                const float v = tk[k];
+                for (int64_t a = g; a < A; a += groups) dx[(a * R + b) * K + k] = v;
+            }
+        }
+    }
+    if (job2) {   // uniform per block: the barrier below is reached by all threads or none
+        if (N < kGsrThreads) {
+            const int n = t % N, rg = t / N;
+            if (rg < G) {
+                float acc = 0.f;
+                for (int64_t r = rg; r < R; r += G) acc = fmaf(xpart[r], ctall[r * N + n], acc);
+                red[rg * N + n] = acc;
+            }
+            __syncthreads();
+            if (t < N) {
+                float acc = red[t];
+                for (int q = 1; q < G; ++q) acc += red[q * N + t];
+                dy[(int64_t)b * N + t] = acc;
+            }
+        } else {
+            for (int n = t; n < N; n += kGsrThreads) {
+                float acc = 0.f;
+                for (int64_t r = 0; r < R; ++r) acc = fmaf(xpart[r], ctall[r * N + n], acc);
+                dy[(int64_t)b * N + n] = acc;
+            }
+        }
+    }
+}
+size_t gsr_vjp_det_smem(int64_t R, int K, int N) {
+    const int64_t RT = R < kGsrThreads ? R : kGsrThreads;
+    return sizeof(float) * ((size_t)K * (N + 1) + N + K + (size_t)R * N + (size_t)(kGsrThreads / RT) * R + (size_t)(N < kGsrThreads ? kGsrThreads / N : 1) * N);
+}
+
 // ====================================================================== launch wrappers
 namespace {
 __global__ void k_mc_push(const float* __restrict__ src, float* out_mc, int64_t n) {
@@ -850,16 +1029,46 @@ size_t gsr_vjp_smem(int K, int N) { return sizeof(float) * ((size_t)K * (N + 1) 
 bool gsr_fits(int64_t K, int64_t N) { return K >= 1 && N >= 1 && K <= 1024 && N <= 4096 && gsr_vjp_smem((int)K, (int)N) <= 96 * 1024; }
 void gsr_fwd(const LaunchCtx& lc, const float* x, const float* y, float* out, int64_t A, int64_t R, int K, int N) {
     const int KT = K < kGsrThreads ? K : kGsrThreads;
+    const size_t staged = gsr_fwd_staged_smem(K, N);
+    if (staged <= 96 * 1024) {
+        static unsigned long long done_mask = 0;      // opt-in above 48 KiB, once per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (staged > 48 * 1024 && (dev >= 64 || !((done_mask >> dev) & 1ull))) {
+            cudaFuncSetAttribute(k_gsr_fwd_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (dev < 64) done_mask |= 1ull << dev;
+        }
+        k_gsr_fwd_staged<<<(unsigned)R, kGsrThreads, staged, lc.stream>>>(x, y, out, A, R, K, N);
+        count(lc);
+        return;
+    }
     k_gsr_fwd<<<(unsigned)R, kGsrThreads, sizeof(float) * (size_t)(kGsrThreads / KT) * K, lc.stream>>>(x, y, out, A, R, K, N);
     count(lc);
 }
+bool gsr_vjp_needs_zeroed_dy(int64_t R, int K, int N) { return !(R <= 4096 && gsr_vjp_det_smem(R, K, N) <= 96 * 1024); }
 void gsr_vjp(const LaunchCtx& lc, const float* x, const float* y, const float* ct, float* dx, float* dy, int64_t A, int64_t R, int K, int N) {
+    if (!gsr_vjp_needs_zeroed_dy(R, K, N)) {
+        const size_t smem_det = gsr_vjp_det_smem(R, K, N);
+        static unsigned long long det_mask = 0;       // opt-in above 48 KiB, once per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (smem_det > 48 * 1024 && (dev >= 64 || !((det_mask >> dev) & 1ull))) {
+            cudaFuncSetAttribute(k_gsr_vjp_det, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (dev < 64) det_mask |= 1ull << dev;
+        }
+        const unsigned grid = (unsigned)(R > K ? R : K);
+        k_gsr_vjp_det<<<grid, kGsrThreads, smem_det, lc.stream>>>(x, y, ct, dx, dy, A, R, K, N);
+        count(lc);
+        return;
+    }
     const size_t smem = gsr_vjp_smem(K, N);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done_mask = 0;     // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !((attr_done_mask >> dev) & 1ull)) {
         cudaFuncSetAttribute(k_gsr_vjp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(k_gsr_vjp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_done = true;
+        if (dev < 64) attr_done_mask |= 1ull << dev;
     }
     // rows per CTA: one, until there are more rows than 4 waves of CTAs (measured at R = 64: 4 rows per CTA is 1.8x SLOWER — the rows
     // of one CTA are serialised latency chains, and the K*N reds per CTA were never the bottleneck)

@@ -79,6 +79,7 @@ void diag_extract(const LaunchCtx&, const float* a, float* out, int64_t n, int r
 bool gsr_fits(int64_t K, int64_t N);
 void gsr_fwd(const LaunchCtx&, const float* x, const float* y, float* out, int64_t A, int64_t R, int K, int N);
 void gsr_vjp(const LaunchCtx&, const float* x, const float* y, const float* ct, float* dx, float* dy, int64_t A, int64_t R, int K, int N);
+bool gsr_vjp_needs_zeroed_dy(int64_t R, int K, int N);   // false: the deterministic kernel writes every element of dy itself
 
 // ---- losses / softmax (rows = samples)
 void softmax_rows(const LaunchCtx&, const float* Z, float* A, int64_t rows, int64_t cols);   // exp / sum exp, no max-subtraction (NeuralNet.hs:52-59)

@@ -220,6 +220,28 @@ def test_mlp_output_layer_skinny_products(ctx, B, hidden, classes):
     close(ctx.from_numpy(H).gemm(CuTensor.transp(ctx.from_numpy(Ws[1]))), H @ Ws[1].T, 1e-5, "thin-N product")
 
 
+def test_narrow_output_layer_on_the_tcgen05_route():
+    """TOPS_SKINNY=0 keeps products with a dimension <= 16 on the tensor-core path (fp16 planes with padded rows), the route they took
+    before the streaming kernels existed: same netGrad, same tolerance."""
+    os.environ["TOPS_SKINNY"] = "0"
+    try:
+        c2 = tb.Context(0)
+    finally:
+        del os.environ["TOPS_SKINNY"]
+    rng = np.random.default_rng(77)
+    f = lambda a: a.astype(np.float32).astype(np.float64)
+    dims, B = [48, 64, 10], 1000
+    Ws = [f(rng.normal(0, 1 / np.sqrt(dims[l]), (dims[l + 1], dims[l]))) for l in range(2)]
+    bs = [f(rng.normal(0, 0.5, dims[l + 1])) for l in range(2)]
+    X = f(rng.uniform(0, 1, (B, dims[0]))); Y = f(np.eye(10)[rng.integers(0, 10, B)])
+    ref = O.mlp_dense_fwd_grad(X, Ws, bs, ["logistic", "softmax"], "crossEntropy", Y)
+    A, L, dX, dWs, dbs = nn.mlp_fwd_grad([c2.from_numpy(w) for w in Ws], [c2.from_numpy(b) for b in bs], [tb.ACT_LOGISTIC, tb.ACT_SOFTMAX],
+                                         tb.LOSS_CROSS_ENTROPY, c2.from_numpy(X), c2.from_numpy(Y))
+    close(A, ref[0], 1e-5, "A"); close(dX, ref[2], 1e-5, "dX")
+    for l in range(2):
+        close(dWs[l], ref[3][l], 1e-5, f"dW{l}"); close(dbs[l], ref[4][l], 1e-5, f"db{l}")
+
+
 @pytest.mark.parametrize("classes", [20, 32, 40])
 def test_softmax_ce_head_wider_than_the_thread_per_row_kernel(ctx, classes):
     """17..32 classes: warp-per-row head with db fused by lane; more than 32: the head leaves db to the column-sum pass."""
@@ -363,6 +385,24 @@ def test_config5_contraction_full_size(ctx):
     want = O.gradTOp_(oop, [x, y], [ct])
     got = TO.gradTOp_(op, [dx_, dy_], [dct])
     close(got[0], want[0], 1e-5, "dx"); close(got[1], want[1], 1e-5, "dy")
+
+
+@pytest.mark.parametrize("A,R,K,N", [(5, 3, 7, 2), (9, 70, 33, 12), (4, 20, 96, 40), (17, 8, 5, 600), (3, 130, 64, 64), (2, 600, 16, 8)])
+def test_fused_contraction_row_sum_shapes(ctx, A, R, K, N):
+    """gmul (2,1,1) >>> sumRows on ragged shapes: more rows than columns of y and the reverse, N above and below the block size, row
+    counts above it — forward (staged y) and the deterministic VJP (dy written once per element, no zeroing, no reds); the VJP
+    is also bit-reproducible from call to call."""
+    rng = np.random.default_rng(A * 1000 + R * 7 + K + N)
+    x, y, ct = (rng.normal(size=s).astype(np.float32).astype(np.float64) for s in ((A, R, K), (K, N), (R, N)))
+    oop = O.op_gmul(2, 1, 1) >> O.op_sumRows()
+    op = TO.gmul(2, 1, 1) >> TO.sumRows()
+    dx_, dy_, dct = ctx.from_numpy(x), ctx.from_numpy(y), ctx.from_numpy(ct)
+    close(TO.runTOp(op, [dx_, dy_])[0], O.runTOp(oop, [x, y])[0], 1e-5, "z")
+    want = O.gradTOp_(oop, [x, y], [ct])
+    got = TO.gradTOp_(op, [dx_, dy_], [dct])
+    close(got[0], want[0], 1e-5, "dx"); close(got[1], want[1], 1e-5, "dy")
+    again = TO.gradTOp_(op, [dx_, dy_], [dct])
+    assert np.array_equal(got[1].numpy(), again[1].numpy())
 
 
 def test_transp_is_full_axis_reversal(ctx):
