@@ -57,6 +57,11 @@ typedef enum {
                                  accumulation: ~6e-7 rel at 1.5 TF32-pass equivalents (fp16 MMAs run at twice the TF32 rate) */
 } tops_precision;
 
+/* Routing that does not depend on the mode: fp32 products with M, N or K <= 16 (an MLP's output layer) are HBM-bound and run on
+ * streaming CUDA-core kernels in plain fp32 (exact products) in every mode but TOPS_PREC_FP32_SIMT, which keeps its one reference kernel.
+ * Environment overrides read by tops_init (diagnostics, not API): TOPS_SKINNY=0 keeps those products on the tensor-core path;
+ * TOPS_F16X3_CHUNK / TOPS_F16X3_FWD_CHUNK / TOPS_F16X3_FWD_HEAD = k-blocks per TMEM accumulation chunk (accuracy/speed trade-off of
+ * TOPS_PREC_F16X3); TOPS_GEMM_DEBUG bit 0 disables the specialised epilogue code paths of the tcgen05 GEMM. */
 typedef enum { TOPS_ACT_ID = 0, TOPS_ACT_LOGISTIC = 1, TOPS_ACT_SOFTMAX = 2 } tops_act;
 typedef enum { TOPS_LOSS_NONE = 0, TOPS_LOSS_SQUARED_ERROR = 1, TOPS_LOSS_CROSS_ENTROPY = 2 } tops_loss;
 
