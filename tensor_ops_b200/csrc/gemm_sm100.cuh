@@ -945,6 +945,58 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
             ptx::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + half * HC + (static_cast<uint32_t>(q * 32) << 16);
+            // fp32 (single-pass TF32) forward GEMM of the ffLayer step on an interior tile: the specialised block code — same steps as
+            // epi_block without its generality (every epilogue variant, dtype and edge case in one stream), the TMEM load of block
+            // c+1 in flight while block c is processed, and the accumulator buffer handed back as soon as the last load has landed
+            bool lean1 = false;
+            if constexpr (std::is_same<T, float>::value && !Cfg::EPI_SHARED) {
+                lean1 = tma && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && !p.out1_pair && p.colsum != nullptr && p.colsum_src == 2 &&
+                        p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && row0 + 32 <= p.M && n0 + HC <= p.N && !(p.debug & 1);
+                if (lean1) {
+                    uint32_t raw[2][32];
+                    ptx::tmem_ld_32x32b_x32(t_row, raw[0]);
+#pragma unroll
+                    for (int c = 0; c < HC / 32; ++c) {
+                        ptx::tmem_ld_wait();
+                        if (c + 1 < HC / 32) ptx::tmem_ld_32x32b_x32(t_row + (c + 1) * 32, raw[(c + 1) & 1]);
+                        else {                                  // every column of the accumulator is in registers: free the buffer now
+                            ptx::tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) { if constexpr (CG == 2) ptx::mbar_arrive_cluster(tmem_empty0 + acc * 8); else ptx::mbar_arrive(&tmem_empty[acc]); }
+                        }
+                        const int col = n0 + c * 32;
+                        float v[32], x[32];
+                        const float4* b4p = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const float4 b4 = __ldg(b4p + g);
+                            v[g * 4] = act_apply(ACT_LOGISTIC, __uint_as_float(raw[c & 1][g * 4]) + b4.x);
+                            v[g * 4 + 1] = act_apply(ACT_LOGISTIC, __uint_as_float(raw[c & 1][g * 4 + 1]) + b4.y);
+                            v[g * 4 + 2] = act_apply(ACT_LOGISTIC, __uint_as_float(raw[c & 1][g * 4 + 2]) + b4.z);
+                            v[g * 4 + 3] = act_apply(ACT_LOGISTIC, __uint_as_float(raw[c & 1][g * 4 + 3]) + b4.w);
+                        }
+                        if (!ew.in_flight) epi_issue_aux<float, 32>(&tmAux, ew, lane, row0, col);
+                        ptx::mbar_wait(ew.aux_bar, ew.consumed & 1, wd, 0x600);
+                        ++ew.consumed;
+                        stage_read_row<float, 32>(ew.aux_buf, lane, x);
+                        __syncwarp();
+                        ew.in_flight = false;
+                        if (c + 1 < HC / 32) epi_issue_aux<float, 32>(&tmAux, ew, lane, row0, col + 32);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) x[e] = x[e] * (v[e] * (1.0f - v[e]));
+                        stage_write_row<float, 32>(ew.out_buf, lane, v);
+                        __syncwarp();
+                        stage_store_global<float, 32>(ew.out_buf, lane, p.out0, p.ld_out0, row0, col, p.M, p.N);
+                        __syncwarp();
+                        stage_write_row<float, 32>(ew.out_buf, lane, x);
+                        __syncwarp();
+                        stage_colsum<float, 32>(ew.out_buf, lane, col, p.N, p.colsum);
+                        stage_store_global<float, 32>(ew.out_buf, lane, p.out1, p.ld_out1, row0, col, p.M, p.N);
+                        __syncwarp();
+                    }
+                    continue;                                   // next work item (the accumulator was released above)
+                }
+            }
 #pragma unroll 1
             for (int c = 0; c < nblk; ++c) {
                 uint32_t raw[W];
