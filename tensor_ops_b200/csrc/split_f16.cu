@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(kThreads) k_split_f16_rows(const float* __rest
             }
             ymax = max(ymax, __float_as_uint(my));
         }
-        const int e = scale_exp_of(warp_max_u(__float_as_uint(m)));
+        const unsigned m_all = warp_max_u(__float_as_uint(m));
+        const int e = scale_exp_of(m_all);
         const float s = pow2f(13 - e);
         uint2* hr = reinterpret_cast<uint2*>(hi + r * cols);
         uint2* lr = reinterpret_cast<uint2*>(lo + r * cols);
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) k_split_f16_rows(const float* __rest
                 hr[c] = h; lr[c] = l;
             }
         }
-        const float inv = pow2f(e - 13);
+        const float inv = m_all == 0u ? 0.f : pow2f(e - 13);   // all-zero row: marked, its scale is chosen by the fix-up pass
         if (lane == 0) rs[r] = inv;
         rs_max = max(rs_max, __float_as_uint(inv));
     }
@@ -191,14 +192,49 @@ __global__ void __launch_bounds__(kThreads) k_split_f16_rows_generic(const float
         const float* xr = x + r * cols;
         float m = 0.f;
         for (int64_t c = lane; c < cols; c += 32) m = fmaxf(m, fabsf(xr[c]));
-        const int e = scale_exp_of(warp_max_u(__float_as_uint(m)));
+        const unsigned m_all = warp_max_u(__float_as_uint(m));
+        const int e = scale_exp_of(m_all);
         const float s = pow2f(13 - e);
         for (int64_t c = lane; c < cols; c += 32) split1(xr[c], s, hi[r * cols + c], lo[r * cols + c]);
-        const float inv = pow2f(e - 13);
+        const float inv = m_all == 0u ? 0.f : pow2f(e - 13);
         if (lane == 0) rs[r] = inv;
         rs_max = max(rs_max, __float_as_uint(inv));
     }
     if (lane == 0 && rs_max != 0u) atomicMax(max_rs_bits, rs_max);
+}
+
+// Fix-up after the row split, once max_s rs[s] is final.  The cotangent pair is scaled by c * rs[s] (so that the per-sample factors
+// cancel inside dW's contraction over s), with c = 2^13 / (max|dA| max_s rs[s]): a row whose rs is 2^-k of the largest gets a
+// cotangent pair 2^-k below full scale.  Without a bound on k one outlier row (magnitude 1e6 times the others) would push every
+// other row's dZ pair into fp16's subnormals — and their dX with it.  So rows more than kRowScaleSpread binades below the largest
+// are re-split with the scale of the bound (they keep >= 22 - 8 bits of the largest row's resolution, which is what a per-tensor
+// scale would have given them, times 2^8), and all-zero rows (marked rs = 0, planes are zeros under any scale) get the largest rs.
+// In the common case every row passes the test and the pass only reads rs[]: a few microseconds.
+constexpr int kRowScaleSpread = 8;
+__global__ void __launch_bounds__(kThreads) k_split_f16_rows_fixup(const float* __restrict__ x, int64_t rows, int64_t cols, __half* __restrict__ hi,
+                                                                   __half* __restrict__ lo, float* __restrict__ rs, const unsigned* __restrict__ max_rs_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned mb = __ldg(max_rs_bits);
+    const float mr = mb == 0u ? 1.0f : __uint_as_float(mb);              // every row zero: any scale will do
+    const int er = (int)((__float_as_uint(mr) >> 23) & 0xffu) - 127;
+    const int et = er - kRowScaleSpread < -120 ? -120 : er - kRowScaleSpread;
+    const float thr = pow2f(et), s = pow2f(-et);
+    // a warp tests 32 rows with one coalesced load; only rows that fail the test (none, normally) are touched again
+    for (int64_t r0 = warp * 32; r0 < rows; r0 += nwarps * 32) {
+        const int64_t rl = r0 + lane;
+        const float inv = rl < rows ? rs[rl] : mr;
+        if (inv == 0.f) rs[rl] = mr;                                      // all-zero row
+        unsigned todo = __ballot_sync(0xffffffffu, inv != 0.f && inv < thr);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t r = r0 + j;
+            const float* xr = x + r * cols;
+            for (int64_t c = lane; c < cols; c += 32) split1(xr[c], s, hi[r * cols + c], lo[r * cols + c]);
+            if (lane == 0) rs[r] = thr;
+        }
+    }
 }
 
 // The scalars one ffLayer forward + VJP needs (all powers of two):
@@ -268,6 +304,8 @@ void split_f16_rows(const LaunchCtx& lc, const float* x, int64_t rows, int64_t c
     if (!fast) {
         k_split_f16_rows_generic<<<grid, kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits);
         count(lc);
+        k_split_f16_rows_fixup<<<grid_for(lc, (rows + 31) / 32, kThreads / 32, 2), kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits);
+        count(lc);
         if (y != nullptr) absmax_bits(lc, y, rows * ycols, ymax_bits);
         return;
     }
@@ -279,6 +317,8 @@ void split_f16_rows(const LaunchCtx& lc, const float* x, int64_t rows, int64_t c
     else if (c4 <= 256) TOPS_SPLIT_ROWS(8);
     else TOPS_SPLIT_ROWS(16);
 #undef TOPS_SPLIT_ROWS
+    count(lc);
+    k_split_f16_rows_fixup<<<grid_for(lc, (rows + 31) / 32, kThreads / 32, 2), kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits);
     count(lc);
 }
 

@@ -106,6 +106,35 @@ def test_fflayer_identity_activation_and_non_saturating_init(ctx):
         close(t, r, 1e-5, name)
 
 
+def test_fflayer_degenerate_magnitudes(ctx):
+    """The fp16-pair scaling at its corners: an all-zero cotangent (max|dA| = 0), all-zero rows of X, an all-zero W or X, and rows of X
+    whose magnitudes differ by 2^20 (the per-row scales of X and the row factors of the cotangent pair share one budget: DESIGN §2).
+    Parity must hold in all of them; with an absurd spread (rows 1e25 and 1e-25 times the others: beyond any fp16-based scheme) the
+    outputs must at least stay finite."""
+    rng = np.random.default_rng(123)
+    B, i, o = 512, 256, 256
+    f = lambda a: a.astype(np.float32).astype(np.float64)
+    X = f(rng.uniform(-1, 1, (B, i))); X[3] = 0.0; X[200:210] = 0.0
+    W = f(rng.normal(0, 0.05, (o, i))); b = f(rng.normal(0, 0.5, o)); dA = f(rng.normal(size=(B, o)))
+    Xo = X.copy(); Xo[5] *= 1e6; Xo[100] *= 1e-6                     # one outlier row 2^20 above the rest, one 2^20 below
+    Xa = X.copy(); Xa[7] *= 1e25; Xa[11] *= 1e-25
+    cases = {"zero rows": (X, W, dA, True), "dA = 0": (X, W, np.zeros_like(dA), True), "W = 0": (X, np.zeros_like(W), dA, True),
+             "X = 0": (np.zeros_like(X), W, dA, True), "outlier rows": (f(Xo), W, dA, True), "absurd spread": (f(Xa), W, dA, False)}
+    for name, (x, w, da, parity) in cases.items():
+        with np.errstate(over="ignore"):
+            ref = O.fflayer_logistic_dense(x, w, b, da)
+        got = nn.fflayer_fwd_grad(ctx.from_numpy(x), ctx.from_numpy(w), ctx.from_numpy(b), ctx.from_numpy(da))
+        for nm, t, r in zip(("A", "dX", "dW", "db"), got, ref):
+            g = t.numpy()
+            assert np.isfinite(g).all(), f"{name}: {nm} has non-finite values"
+            if not parity:
+                continue
+            if np.linalg.norm(r) == 0.0:
+                assert np.abs(g).max() == 0.0, f"{name}: {nm} should be exactly zero"
+            else:
+                close(t, r, 1e-5, f"{name} {nm}")
+
+
 def test_fflayer_error_behaviour(ctx):
     X = ctx.from_numpy(np.zeros((4, 3))); W = ctx.from_numpy(np.zeros((5, 2))); b = ctx.from_numpy(np.zeros(5))
     with pytest.raises(tb.TopsError) as ei:

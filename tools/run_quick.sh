@@ -1,8 +1,9 @@
 mkdir -p gpurun_out
-timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-extra > gpurun_out/bq.json 2>/dev/null
+timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_q.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_q.log
+tail -4 gpurun_out/pytest_q.log
+timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-extra --no-side > gpurun_out/bq.json 2>/dev/null
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bq.json'))
-print(d['ms_per_step'], d['roofline']['per_kernel_ms'], d['parity']['ok'])
-print(json.dumps(d['throughput_mode'])[:900])
+print(d['ms_per_step'], d['roofline']['per_kernel_ms'], d['parity']['ok'], d['gpu_launches'])
 PY
