@@ -945,11 +945,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else ptx::mbar_wait(&tmem_full[acc], acc_ph, wd, 0x400 + acc);
             ptx::tcgen05_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + half * HC + (static_cast<uint32_t>(q * 32) << 16);
-            // fp32 (single-pass TF32) forward GEMM of the ffLayer step on an interior tile: the specialised block code — same steps as
+            // single-pass (TF32 / bf16) forward GEMM of the ffLayer step on an interior tile: the specialised block code — same steps as
             // epi_block without its generality (every epilogue variant, dtype and edge case in one stream), the TMEM load of block
             // c+1 in flight while block c is processed, and the accumulator buffer handed back as soon as the last load has landed
             bool lean1 = false;
-            if constexpr (std::is_same<T, float>::value && !Cfg::EPI_SHARED) {
+            if constexpr (!std::is_same<T, __half>::value && !Cfg::EPI_SHARED) {   // fp32 (TF32) and bf16 operands: staged blocks have the operand dtype
                 lean1 = tma && p.epi == EPI_BIAS_ACT_DZ && p.act == ACT_LOGISTIC && !p.out1_pair && p.colsum != nullptr && p.colsum_src == 2 &&
                         p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && row0 + 32 <= p.M && n0 + HC <= p.N && !(p.debug & 1);
                 if (lean1) {
@@ -975,23 +975,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             v[g * 4 + 2] = act_apply(ACT_LOGISTIC, __uint_as_float(raw[c & 1][g * 4 + 2]) + b4.z);
                             v[g * 4 + 3] = act_apply(ACT_LOGISTIC, __uint_as_float(raw[c & 1][g * 4 + 3]) + b4.w);
                         }
-                        if (!ew.in_flight) epi_issue_aux<float, 32>(&tmAux, ew, lane, row0, col);
+                        if (!ew.in_flight) epi_issue_aux<T, 32>(&tmAux, ew, lane, row0, col);
                         ptx::mbar_wait(ew.aux_bar, ew.consumed & 1, wd, 0x600);
                         ++ew.consumed;
-                        stage_read_row<float, 32>(ew.aux_buf, lane, x);
+                        stage_read_row<T, 32>(ew.aux_buf, lane, x);
                         __syncwarp();
                         ew.in_flight = false;
-                        if (c + 1 < HC / 32) epi_issue_aux<float, 32>(&tmAux, ew, lane, row0, col + 32);
+                        if (c + 1 < HC / 32) epi_issue_aux<T, 32>(&tmAux, ew, lane, row0, col + 32);
 #pragma unroll
                         for (int e = 0; e < 32; ++e) x[e] = x[e] * (v[e] * (1.0f - v[e]));
-                        stage_write_row<float, 32>(ew.out_buf, lane, v);
+                        stage_write_row<T, 32>(ew.out_buf, lane, v);
                         __syncwarp();
-                        stage_store_global<float, 32>(ew.out_buf, lane, p.out0, p.ld_out0, row0, col, p.M, p.N);
+                        stage_store_global<T, 32>(ew.out_buf, lane, p.out0, p.ld_out0, row0, col, p.M, p.N);
                         __syncwarp();
-                        stage_write_row<float, 32>(ew.out_buf, lane, x);
+                        stage_write_row<T, 32>(ew.out_buf, lane, x);
                         __syncwarp();
-                        stage_colsum<float, 32>(ew.out_buf, lane, col, p.N, p.colsum);
-                        stage_store_global<float, 32>(ew.out_buf, lane, p.out1, p.ld_out1, row0, col, p.M, p.N);
+                        stage_colsum<T, 32>(ew.out_buf, lane, col, p.N, p.colsum);
+                        stage_store_global<T, 32>(ew.out_buf, lane, p.out1, p.ld_out1, row0, col, p.M, p.N);
                         __syncwarp();
                     }
                     continue;                                   // next work item (the accumulator was released above)
