@@ -516,13 +516,17 @@ def main():
     # per-kernel durations for the roofline record: the same K steps once more, now with a CUDA event pair around every tagged
     # kernel (tops_profile_*).  Kept out of the timed region: the events sit between the launches and cost 1.2 % of a step
     # (tools/step_noprofile.py), i.e. a number taken with them would be a number taken under a profiler.
+    if sampler:
+        sampler.active = False
+    torch.cuda.synchronize()
+    time.sleep(1.0)          # same starting conditions as the timed region: the boards power-cap after ~50 back-to-back steps
+    for _ in range(2):
+        step()
     ctx.profile(True)
     for _ in range(args.steps):
         step()
     prof = ctx.profile_summary()
     ctx.profile(False)
-    if sampler:
-        sampler.active = False
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
