@@ -653,7 +653,7 @@ def main():
                        "precision": PREC_TEXT[args.precision],
                        "parallelism": f"dp{world} (batch-sharded, one all-reduce of [dW||db] per step)" if world > 1 else "single GPU",
                        "allreduce": allreduce_kind, "allreduce_trial": allreduce_trial,
-                       "kernels": "per step: fp16-pair split of X (+ max|dA|) and of W, then 3 tcgen05 cta_group::2 GEMMs (CTA pairs, 256x256 tiles): forward with fused bias/logistic/dZ-pair/db epilogue, split-K dW, dX" if args.precision == "f16x3" else "3 per step: tcgen05 cta_group::2 GEMMs (CTA pairs, 256x256 tiles) with fused bias/logistic/dZ/db epilogue, split-K dW, dX",
+                       "kernels": "5 per step: fp16-pair row split of X (+ max|dA|, max|W|), its fix-up pass (+ the pair of W and the layer scalars), then 3 tcgen05 cta_group::2 GEMMs (CTA pairs, 256x256 tiles): forward with fused bias/logistic/dZ-pair/db epilogue, split-K dW, dX" if args.precision == "f16x3" else "3 per step: tcgen05 cta_group::2 GEMMs (CTA pairs, 256x256 tiles) with fused bias/logistic/dZ/db epilogue, split-K dW, dX",
                        "l2": "inputs larger than L2: X and dA are 256 MiB each per step vs 126 MB L2"},
             "roofline": roofline, "parity": parity, "gpu_launches": int(launches), "clocks": clocks,
             "algorithmic_flop_per_step": 6.0 * B * i * o, "tflops_step": 6.0 * B * i * o / (ms_per_step * 1e-3) / 1e12}

@@ -1131,13 +1131,15 @@ int dw_db(tops_ctx* ctx, const LayerShapes& s, const void* dZ, const void* Xin, 
 //   dW GEMM         sum_s dZ'[s,o] X'[s,i] = c * dW: the per-sample factors cancel inside the contraction
 //   dX GEMM         dX[s,:] = acc / (c sW rsX[s])
 // c = 2^(13 - e(max|dA|)) / max_s rsX[s] keeps |dZ'| < 2^14 (|act'| <= 1).  All factors are powers of two: the scaling is exact.
-struct WPairF16 { void* w1 = nullptr; void* w2 = nullptr; float* s2 = nullptr; };
+// fp16 pair of a layer's W.  `pending`: the planes are allocated but not written yet — the split rides along with the two launches
+// of the X row split inside layer_fwd_grad_f16x3 (max|W| with the rows, the pair with the fix-up pass) instead of two of its own.
+struct WPairF16 { void* w1 = nullptr; void* w2 = nullptr; float* s2 = nullptr; bool pending = false; const float* src = nullptr; int64_t n = 0; unsigned* mx = nullptr; };
 
 bool f16x3_layer_ok(tops_ctx* ctx, const LayerShapes& s) {
     return ctx->precision == TOPS_PREC_F16X3 && s.dtype == TOPS_F32 && s.B > 0 && s.i > 0 && s.o > 0 && (s.i % 8) == 0 && (s.o % 8) == 0;
 }
 
-int prep_wpair_f16(tops_ctx* ctx, const LayerShapes& s, const void* W, Tmp& tmp, WPairF16* out) {
+int prep_wpair_f16(tops_ctx* ctx, const LayerShapes& s, const void* W, Tmp& tmp, WPairF16* out, bool defer = false) {
     int64_t pd[1] = {s.o * s.i}, sd[1] = {4};
     tops_buf *hi = nullptr, *lo = nullptr, *sc = nullptr;
     TRY(alloc_buf(ctx, TOPS_BF16, 1, pd, &hi)); tmp.keep(hi);
@@ -1145,6 +1147,10 @@ int prep_wpair_f16(tops_ctx* ctx, const LayerShapes& s, const void* W, Tmp& tmp,
     TRY(alloc_buf(ctx, TOPS_F32, 1, sd, &sc)); tmp.keep(sc);
     unsigned* mx = reinterpret_cast<unsigned*>(sc->data) + 2;
     CUDA_TRY(ctx, cudaMemsetAsync(mx, 0, 4, ctx->stream));
+    if (defer) {
+        *out = WPairF16{hi->data, lo->data, (float*)sc->data, true, (const float*)W, s.o * s.i, mx};
+        return TOPS_OK;
+    }
     ProfScope prof_(ctx, "split_f16_W", 0.0, 12.0 * (double)s.o * s.i);
     k::absmax_bits(lc_of(ctx), (const float*)W, s.o * s.i, mx);
     k::split_f16_tensor(lc_of(ctx), (const float*)W, s.o * s.i, mx, hi->data, lo->data, (float*)sc->data);
@@ -1172,9 +1178,11 @@ int layer_fwd_grad_f16x3(tops_ctx* ctx, const LayerShapes& s, const void* X, con
     const float* rsX = (const float*)rs->data;
     CUDA_TRY(ctx, cudaMemsetAsync(words, 0, 8, ctx->stream));
     {
-        ProfScope prof_(ctx, "split_f16_X", 0.0, 8.0 * (double)s.B * s.i + 4.0 * (double)s.B * s.o);
-        k::split_f16_rows(lc_of(ctx), (const float*)X, s.B, s.i, x1->data, x2->data, (float*)rs->data, words, (const float*)dA, s.o, words + 1);
-        k::f16x3_layer_scales(lc_of(ctx), words, words + 1, wp.s2, scal);
+        ProfScope prof_(ctx, "split_f16_X", 0.0, 8.0 * (double)s.B * s.i + 4.0 * (double)s.B * s.o + (wp.pending ? 12.0 * (double)s.o * s.i : 0.0));
+        // two launches: rows of X (+ max|dA|, + max|W|), then the fix-up pass (+ the pair of W, + the layer's scalars)
+        k::SideTensor side{wp.pending ? wp.src : nullptr, wp.n, wp.mx, wp.w1, wp.w2, wp.s2};
+        k::split_f16_rows(lc_of(ctx), (const float*)X, s.B, s.i, x1->data, x2->data, (float*)rs->data, words, (const float*)dA, s.o, words + 1,
+                          wp.pending ? &side : nullptr, wp.s2, scal);
         TRY(check_launch(ctx, "split_f16(X)"));
     }
     // ---- forward: A, db, (dZ1, dZ2)
@@ -1258,7 +1266,7 @@ extern "C" int tops_fflayer_fwd_grad(tops_ctx* ctx, const tops_buf* X, const top
     if (db) TRY(prep_out(ctx, db, TOPS_F32, 1, dbs));
     Tmp tmp;
     if (f16x3_layer_ok(ctx, s)) {
-        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp));
+        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp, true));
         return layer_fwd_grad_f16x3(ctx, s, X->data, wp, b ? (const float*)b->data : nullptr, act, dA->data, (*A)->data, dX ? (*dX)->data : nullptr,
                                     (float*)(*dW)->data, db ? (float*)(*db)->data : nullptr, false, nullptr);
     }
@@ -1370,7 +1378,7 @@ extern "C" int tops_fflayer_fwd_grad_mc(tops_ctx* ctx, const tops_buf* X, const 
     float* dW_mc = (float*)grads_mc; float* db_mc = dW_mc + s.o * s.i;
     Tmp tmp;
     if (f16x3_layer_ok(ctx, s)) {
-        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp));
+        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp, true));
         TRY(layer_fwd_grad_f16x3(ctx, s, X->data, wp, b ? (const float*)b->data : nullptr, act, dA->data, (*A)->data, dX ? (*dX)->data : nullptr, dW, db, false, dW_mc));
         k::mc_push(lc_of(ctx), db, db_mc, s.o);
         return check_launch(ctx, "mc_push");
@@ -1496,7 +1504,7 @@ extern "C" int tops_fflayer_step_dp(tops_ctx* ctx, const tops_buf* X, const tops
         return TOPS_OK;
     }
     if (f16x3_layer_ok(ctx, s)) {
-        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp));
+        WPairF16 wp; TRY(prep_wpair_f16(ctx, s, W->data, tmp, &wp, true));
         return layer_fwd_grad_f16x3(ctx, s, X->data, wp, b ? (const float*)b->data : nullptr, act, dA->data, (*A)->data, dX ? (*dX)->data : nullptr,
                                     dW, db, false, nullptr, ev, dx_ctas);
     }

@@ -38,8 +38,13 @@ void split_f16_tensor_2d(const LaunchCtx&, const float* x, int64_t rows, int64_t
 void f16x3_pair_scale(const LaunchCtx&, const float* sa2, const float* sb2, float* out);
 // one scale per row: rs[r] = 1/scale_r; max_rs_bits (PRE-ZEROED) = max_r rs[r] as fp32 bits.  y (nullable, [rows, ycols]):
 // max |y| is reduced into the PRE-ZEROED ymax_bits by the same launch
+// A small second tensor (the layer's W) whose max|.| and fp16 pair ride along with the two launches of the row split
+struct SideTensor { const float* w; int64_t n; unsigned* mx; void* hi; void* lo; float* scale2; };
+// ... + fix-up pass (row-scale spread, zero rows).  Optional riders of the same two launches: `side` (see SideTensor) and the layer's
+// scalars (scales_out4 = {1/sW, c, 1/c, 1/(c sW)}, from max rs, max|y| and sW2[1] — or the side tensor's scale when it rides along)
 void split_f16_rows(const LaunchCtx&, const float* x, int64_t rows, int64_t cols, void* hi, void* lo, float* rs, unsigned* max_rs_bits,
-                    const float* y, int64_t ycols, unsigned* ymax_bits);
+                    const float* y, int64_t ycols, unsigned* ymax_bits, const SideTensor* side = nullptr, const float* sW2 = nullptr,
+                    float* scales_out4 = nullptr);
 // out4 = {1/sW, c, 1/c, 1/(c sW)}: the device scalars of one F16X3 ffLayer forward + VJP (sW2 = {sW, 1/sW}, nullable)
 void f16x3_layer_scales(const LaunchCtx&, const unsigned* max_rs_bits, const unsigned* absmax_dA_bits, const float* sW2, float* out4);
 

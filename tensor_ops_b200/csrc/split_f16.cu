@@ -27,6 +27,10 @@ __device__ __forceinline__ int scale_exp_of(unsigned abs_bits) {
 }
 __device__ __forceinline__ float pow2f(int e) { return __uint_as_float((unsigned)(127 + e) << 23); }
 
+// A small second tensor (the layer's W) that rides along with the row split of X instead of taking two launches of its own:
+// its max|.| is reduced by the row-split launch, its fp16 pair is written by the fix-up launch.
+struct SideSplit { const float* w; int64_t n; unsigned* mx; __half* hi; __half* lo; float* scale2; };
+
 __device__ __forceinline__ unsigned warp_max_u(unsigned v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -133,10 +137,21 @@ __global__ void k_f16x3_pair_scale(const float* __restrict__ sa2, const float* _
 template <int NV>
 __global__ void __launch_bounds__(kThreads) k_split_f16_rows(const float* __restrict__ x, int64_t rows, int64_t cols, __half* __restrict__ hi,
                                                              __half* __restrict__ lo, float* __restrict__ rs, unsigned* __restrict__ max_rs_bits,
-                                                             const float* __restrict__ y, int64_t ycols, unsigned* __restrict__ ymax_bits) {
+                                                             const float* __restrict__ y, int64_t ycols, unsigned* __restrict__ ymax_bits, SideSplit side) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t c4 = cols >> 2;    // cols % 4 == 0 and 16-byte aligned rows are guaranteed by the launcher for NV > 0
+    if (side.w != nullptr) {         // max |W| (16-byte aligned, n % 4 == 0: checked by the launcher)
+        const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+        const float4* w4 = reinterpret_cast<const float4*>(side.w);
+        unsigned m = 0u;
+        for (int64_t i = tid; i < (side.n >> 2); i += stride) {
+            const float4 a = __ldg(w4 + i);
+            m = max(m, __float_as_uint(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)))));
+        }
+        m = warp_max_u(m);
+        if (lane == 0 && m != 0u) atomicMax(side.mx, m);
+    }
     unsigned rs_max = 0u, ymax = 0u;
     for (int64_t r = warp; r < rows; r += nwarps) {
         const float4* xr = reinterpret_cast<const float4*>(x + r * cols);
@@ -212,8 +227,36 @@ __global__ void __launch_bounds__(kThreads) k_split_f16_rows_generic(const float
 // In the common case every row passes the test and the pass only reads rs[]: a few microseconds.
 constexpr int kRowScaleSpread = 8;
 __global__ void __launch_bounds__(kThreads) k_split_f16_rows_fixup(const float* __restrict__ x, int64_t rows, int64_t cols, __half* __restrict__ hi,
-                                                                   __half* __restrict__ lo, float* __restrict__ rs, const unsigned* __restrict__ max_rs_bits) {
+                                                                   __half* __restrict__ lo, float* __restrict__ rs, const unsigned* __restrict__ max_rs_bits,
+                                                                   SideSplit side, const unsigned* __restrict__ absmax_dA_bits, const float* __restrict__ sW2,
+                                                                   float* __restrict__ scales_out) {
     const int lane = threadIdx.x & 31;
+    {   // riders of this launch: the fp16 pair of the side tensor (its max is final since the previous launch) and the layer's scalars
+        const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+        float inv_sW = sW2 != nullptr ? sW2[1] : 1.0f;
+        if (side.w != nullptr) {
+            const int e = scale_exp_of(__ldg(side.mx));
+            const float sw = pow2f(13 - e);
+            inv_sW = pow2f(e - 13);
+            if (tid == 0 && side.scale2 != nullptr) { side.scale2[0] = sw; side.scale2[1] = inv_sW; }
+            const float4* w4 = reinterpret_cast<const float4*>(side.w);
+            uint2* h2 = reinterpret_cast<uint2*>(side.hi);
+            uint2* l2 = reinterpret_cast<uint2*>(side.lo);
+            for (int64_t i = tid; i < (side.n >> 2); i += stride) {
+                uint2 h, l;
+                split4(__ldg(w4 + i), sw, h, l);
+                h2[i] = h; l2[i] = l;
+            }
+        }
+        if (scales_out != nullptr && tid == 0) {          // see k_f16x3_layer_scales
+            const int eD = scale_exp_of(*absmax_dA_bits);
+            const unsigned rb = *max_rs_bits;
+            const int eR = rb == 0u ? 0 : (int)((rb >> 23) & 0xffu) - 127;
+            int ec = 13 - eD - eR;
+            ec = ec < -120 ? -120 : (ec > 120 ? 120 : ec);
+            scales_out[0] = inv_sW; scales_out[1] = pow2f(ec); scales_out[2] = pow2f(-ec); scales_out[3] = pow2f(-ec) * inv_sW;
+        }
+    }
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const unsigned mb = __ldg(max_rs_bits);
     const float mr = mb == 0u ? 1.0f : __uint_as_float(mb);              // every row zero: any scale will do
@@ -296,21 +339,35 @@ void f16x3_pair_scale(const LaunchCtx& lc, const float* sa2, const float* sb2, f
 }
 
 void split_f16_rows(const LaunchCtx& lc, const float* x, int64_t rows, int64_t cols, void* hi, void* lo, float* rs, unsigned* max_rs_bits,
-                    const float* y, int64_t ycols, unsigned* ymax_bits) {
+                    const float* y, int64_t ycols, unsigned* ymax_bits, const SideTensor* side_in, const float* sW2, float* scales_out4) {
     if (rows <= 0 || cols <= 0) return;
     const bool fast = (cols % 4) == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7) == 0 &&
                       cols <= 128 * 16 && (y == nullptr || ((ycols % 4) == 0 && aligned16(y)));
     const int grid = grid_for(lc, rows, kThreads / 32, 8);
+    const int grid_fix = grid_for(lc, (rows + 31) / 32, kThreads / 32, 2);
+    // the side tensor rides along only in its vectorised form; otherwise (and on the generic row path) it takes its own two launches
+    SideSplit side{nullptr, 0, nullptr, nullptr, nullptr, nullptr};
+    bool side_own = false;
+    if (side_in != nullptr && side_in->w != nullptr && side_in->n > 0) {
+        if (fast && (side_in->n % 4) == 0 && aligned16(side_in->w) && (reinterpret_cast<uintptr_t>(side_in->hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(side_in->lo) & 7) == 0)
+            side = SideSplit{side_in->w, side_in->n, side_in->mx, (__half*)side_in->hi, (__half*)side_in->lo, side_in->scale2};
+        else side_own = true;
+    }
+    if (side_own) {
+        absmax_bits(lc, side_in->w, side_in->n, side_in->mx);
+        split_f16_tensor(lc, side_in->w, side_in->n, side_in->mx, side_in->hi, side_in->lo, side_in->scale2);
+        sW2 = side_in->scale2;
+    }
     if (!fast) {
         k_split_f16_rows_generic<<<grid, kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits);
         count(lc);
-        k_split_f16_rows_fixup<<<grid_for(lc, (rows + 31) / 32, kThreads / 32, 2), kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits);
-        count(lc);
         if (y != nullptr) absmax_bits(lc, y, rows * ycols, ymax_bits);
+        k_split_f16_rows_fixup<<<grid_fix, kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits, side, ymax_bits, sW2, scales_out4);
+        count(lc);
         return;
     }
     const int64_t c4 = cols / 4;
-#define TOPS_SPLIT_ROWS(NV) k_split_f16_rows<NV><<<grid, kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits, y, ycols, ymax_bits)
+#define TOPS_SPLIT_ROWS(NV) k_split_f16_rows<NV><<<grid, kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits, y, ycols, ymax_bits, side)
     if (c4 <= 32) TOPS_SPLIT_ROWS(1);
     else if (c4 <= 64) TOPS_SPLIT_ROWS(2);
     else if (c4 <= 128) TOPS_SPLIT_ROWS(4);
@@ -318,7 +375,7 @@ void split_f16_rows(const LaunchCtx& lc, const float* x, int64_t rows, int64_t c
     else TOPS_SPLIT_ROWS(16);
 #undef TOPS_SPLIT_ROWS
     count(lc);
-    k_split_f16_rows_fixup<<<grid_for(lc, (rows + 31) / 32, kThreads / 32, 2), kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits);
+    k_split_f16_rows_fixup<<<grid_fix, kThreads, 0, lc.stream>>>(x, rows, cols, (__half*)hi, (__half*)lo, rs, max_rs_bits, side, ymax_bits, sW2, scales_out4);
     count(lc);
 }
 
