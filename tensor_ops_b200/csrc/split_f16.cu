@@ -344,7 +344,7 @@ void split_f16_rows(const LaunchCtx& lc, const float* x, int64_t rows, int64_t c
     const bool fast = (cols % 4) == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7) == 0 &&
                       cols <= 128 * 16 && (y == nullptr || ((ycols % 4) == 0 && aligned16(y)));
     const int grid = grid_for(lc, rows, kThreads / 32, 8);
-    const int grid_fix = grid_for(lc, (rows + 31) / 32, kThreads / 32, 2);
+    int grid_fix = grid_for(lc, (rows + 31) / 32, kThreads / 32, 2);
     // the side tensor rides along only in its vectorised form; otherwise (and on the generic row path) it takes its own two launches
     SideSplit side{nullptr, 0, nullptr, nullptr, nullptr, nullptr};
     bool side_own = false;
@@ -352,6 +352,10 @@ void split_f16_rows(const LaunchCtx& lc, const float* x, int64_t rows, int64_t c
         if (fast && (side_in->n % 4) == 0 && aligned16(side_in->w) && (reinterpret_cast<uintptr_t>(side_in->hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(side_in->lo) & 7) == 0)
             side = SideSplit{side_in->w, side_in->n, side_in->mx, (__half*)side_in->hi, (__half*)side_in->lo, side_in->scale2};
         else side_own = true;
+    }
+    if (side.w != nullptr) {   // the rider's 16-byte pieces, one per thread, decide the grid of the fix-up launch
+        const int g2 = grid_for(lc, side.n / 4, kThreads, 8);
+        if (g2 > grid_fix) grid_fix = g2;
     }
     if (side_own) {
         absmax_bits(lc, side_in->w, side_in->n, side_in->mx);

@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_q.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_q.log
-tail -4 gpurun_out/pytest_q.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -k "fflayer or config2 or cta_pair or host" > gpurun_out/pytest_q.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_q.log
+tail -3 gpurun_out/pytest_q.log
 timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-side --no-extra > gpurun_out/bq.json 2>/dev/null
 python - <<'PY'
 import json
